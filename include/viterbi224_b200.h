@@ -1,0 +1,94 @@
+/*
+ * viterbi224_b200.h -- extensions of libviterbi224_b200 beyond the reference's nine entry
+ * points (include/viterbi224.h).  Plain C ABI: pointers and sizes only.
+ *
+ * Why they exist: the reference's streaming caller, vdecode.c:142-158, forces one synchronous
+ * update(1) + decodebit(delay, 0) pair per decoded bit through the ABI.  That works here as a
+ * drop-in, but a GPU needs work in blocks.  v224x_stream_decode() is that loop in block form;
+ * its output is byte-for-byte what the per-bit loop returns.  The *_dev variants take device
+ * pointers so that a caller (bench.py's `value` leg) can keep the symbol stream resident in HBM.
+ */
+#ifndef VITERBI224_B200_EXT_H
+#define VITERBI224_B200_EXT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device selection / diagnostics -------------------------------------------------- */
+int         v224x_device_count(void);            /* CUDA devices visible, 0 if none              */
+int         v224x_set_device(int dev);           /* device used by subsequent create calls       */
+const char *v224x_last_error(void);              /* text of the last failure in this thread      */
+const char *v224x_version(void);
+
+/* ---- block-mode equivalents of the reference call patterns ---------------------------- */
+
+/* Equivalent to, for i in [0, nbits):
+ *     update_viterbi224_blk(p, syms + 2*i, 1);
+ *     bits_out[i] = decodebit_viterbi224(p, delay, 0);          (vdecode.c:145,152)
+ * with decision rows older than the last init reading as zero (a freshly created reference
+ * ring).  bits_out[i] is 0 or 1.  The ring given to create_viterbi224() must hold more than
+ * `delay` rows; the call works through the stream in chunks of (len - delay) stages.
+ * Returns the number of renormalisations (sum of the per-bit update return values), -1 on error. */
+int v224x_stream_decode(void *p, const unsigned char *syms, int nbits, int delay, unsigned char *bits_out);
+
+/* Same, with syms and bits_out in device memory of the decoder's GPU. */
+int v224x_stream_decode_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out);
+
+/* update_viterbi224_blk with the symbols already in device memory. */
+int v224x_update_dev(void *p, const unsigned char *dev_syms, int nbits);
+
+/* init variant for time-segmented decoding: every metric = SHRT_MIN + bias and no state is
+ * favoured (start_state < 0), or init_viterbi224 semantics (start_state >= 0). */
+int v224x_init_uniform(void *p, int bias, int start_state);
+
+/* ---- device memory helpers for callers without a CUDA runtime of their own ------------ */
+void *v224x_dev_alloc(void *p, size_t bytes);
+void  v224x_dev_free(void *p, void *dev_ptr);
+int   v224x_h2d(void *p, void *dev_dst, const void *host_src, size_t bytes);
+int   v224x_d2h(void *p, void *host_dst, const void *dev_src, size_t bytes);
+void *v224x_host_alloc_pinned(size_t bytes);
+void  v224x_host_free_pinned(void *host_ptr);
+
+/* ---- timing on the decoder's own CUDA stream ------------------------------------------ */
+int   v224x_timer_start(void *p);                /* record an event on the decoder's stream      */
+float v224x_timer_stop_ms(void *p);              /* record + synchronise, elapsed milliseconds   */
+/* Accumulated device time of the ACS pass kernels alone since the last reset (events around
+ * every ACS launch batch), and the number of launches. */
+int   v224x_kernel_time_reset(void *p);
+int   v224x_kernel_time_enable(void *p, int on);
+float v224x_kernel_time_ms(void *p, unsigned long long *n_acs_launches);
+
+/* ---- counters --------------------------------------------------------------------------- */
+typedef struct {
+    unsigned long long launches;       /* kernels launched by this handle since create          */
+    unsigned long long fused_passes;   /* 8-stage passes executed                               */
+    unsigned long long careful_passes; /* ... of which recorded per-stage minima                */
+    unsigned long long single_stages;  /* 1-stage passes (fast arithmetic)                      */
+    unsigned long long sat_stages;     /* 1-stage passes (exact saturating arithmetic)          */
+    unsigned long long chainback_redo; /* speculative chainback segments that had to be redone  */
+    long long          renormals;      /* the reference's `renormals` accumulator               */
+    long long          stages;         /* trellis stages since the last init                    */
+} v224x_stats;
+int v224x_get_stats(void *p, v224x_stats *out);
+
+/* ---- test hooks (state inspection; used by tests/ for parity, not by applications) ------ */
+/* Path metrics as the reference holds them (int16, reference domain), 2^23 values. */
+int v224x_get_metrics(void *p, int16_t *host_out);
+/* Load a mid-stream state: metrics (reference domain), renormals, stages since init. */
+int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, long long stages);
+/* One decision row (0 <= row < len) in the reference's layout: 2^18 words, bit s of the row =
+ * decision of new state s (viterbi224_sse2.c:141). */
+int v224x_get_row(void *p, int row, uint32_t *host_out);
+/* Knobs: "force_single"=1 never fuse, "force_sat"=1 exact saturating single stages only,
+ * "force_careful"=1 always record per-stage minima, "chain_seg"/"chain_warm" chainback
+ * segment length / warm-up depth. */
+int v224x_set_option(void *p, const char *key, long long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITERBI224_B200_EXT_H */

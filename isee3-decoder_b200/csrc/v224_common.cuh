@@ -1,0 +1,82 @@
+// v224_common.cuh -- shared definitions of the B200 viterbi224 runtime and kernels.
+//
+// Code parameters follow the reference's active code block (code.h:54-63, MCQLI-24).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace v224 {
+
+constexpr int      K        = 24;                  // code.h:61
+constexpr uint32_t POLY1    = 073665667u;          // code.h:59
+constexpr uint32_t POLY2    = 073665665u;          // code.h:60
+constexpr int      G1FLIP   = 0;                   // code.h:62
+constexpr int      G2FLIP   = 1;                   // code.h:63
+constexpr uint32_t NSTATES  = 1u << (K - 1);       // 2^23 path metrics
+constexpr uint32_t NBFLY    = 1u << (K - 2);       // 2^22 butterflies per stage
+constexpr uint32_t STATEMASK = NSTATES - 1;
+constexpr uint32_t ROWWORDS = NSTATES / 32;        // 2^18 words = 1 MiB per decision row
+constexpr size_t   ROWBYTES = ROWWORDS * 4;
+constexpr size_t   METRICBYTES = (size_t)NSTATES * 2;   // 16 MiB
+
+constexpr int RENORM_TRIGGER = 25000;              // viterbi224_sse2.c:351
+constexpr int INIT_BIAS      = 5000;               // viterbi224_sse2.c:45 (SHRT_MIN+5000)
+
+// Fused pass geometry: FK stages per HBM pass, done as two register rounds of FR stages.
+constexpr int FR = 4;
+constexpr int FK = 2 * FR;                         // 8 trellis stages per pass
+constexpr int FUSED_TILE_COLS = 64;                // columns (j) per tile
+constexpr int FUSED_THREADS   = 128;               // 16 row-groups x 8 column groups
+constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512
+
+// Decision-row formats (row_fmt[] tags).  0 = canonical (bit index = new-state number, the
+// reference's layout, viterbi224_sse2.c:141,324); t in 1..FK = written by stage t of a fused
+// pass in that kernel's thread-major layout (see fused_bit_address()).
+constexpr uint8_t ROWFMT_CANON = 0;
+
+// Device-resident control block.  One per decoder handle.  The last CTA of every pass
+// ("resolver") folds the pass's statistics into it; the host only reads it back at the end of
+// an ABI call.
+//
+// Metric representation: HBM holds P (uint16, unsigned).  The reference's int16 metric is
+// R = P + O for the 64-bit offset O below.  Decisions depend on metric differences only, so
+// any O is exact as long as neither side saturates; the resolver tracks the reference's
+// renormalisation test (viterbi224_sse2.c:351-377) on R virtually and keeps P small.
+struct Ctl {
+    long long O;            // R = P + O
+    long long renormals;    // the reference's running `renormals` (viterbi224_sse2.c:33,367)
+    long long T;            // trellis stages since init (ring position = T % len)
+    int  pos;               // stages completed within the current update call
+    int  renorm_count;      // renormalisations within the current update call (return value)
+    int  sub;               // amount the next pass subtracts from every P while loading
+    int  cur;               // which metric buffer is the "old" one
+    long long R0;           // reference metric of state 0 after the last stage (renorm trigger watch)
+    long long maxR;         // largest reference metric after the last stage (saturation watch)
+    int  error;             // sticky: internal invariant violated
+    unsigned ticket;        // CTA completion counter of the running pass
+    // per-pass statistics, reset by the resolver
+    unsigned s0[FK + 1];    // P of state 0 after stage t (t = 1..k)
+    unsigned minP[FK + 1];  // global min of P after stage t (careful passes; [k] always)
+    unsigned maxP_end;      // global max of P after the last stage
+    // counters for tests / bench
+    unsigned n_fused, n_single, n_careful, n_sat;
+};
+
+// where a fused-format decision bit lives: stage t (1..FK), state s after that stage.
+// Returns the bit index inside the 2^23-bit row.
+__host__ __device__ inline uint32_t fused_bit_address(int t, uint32_t s)
+{
+    // slot p = state rotated right by t (the slot that held the state's ancestor tile position)
+    uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;
+    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, tau = (p >> 6) & 511, g = (p >> 3) & 7;
+    uint32_t q = (p >> 1) & 3, h = p & 1;
+    uint32_t thr   = (t <= FR) ? ml : mh;       // thread row-group in this round
+    uint32_t inner = (t <= FR) ? mh : ml;       // register row index in this round
+    uint32_t chunk = tau * FUSED_THREADS + thr * 8 + g;          // 16-byte chunk per thread
+    uint32_t w     = inner >> 2;                                  // word in chunk
+    uint32_t i     = ((inner & 3) << 1) | (q >> 1);               // bit in byte
+    uint32_t byte  = ((q & 1) << 1) | h;                          // byte in word
+    return chunk * 128 + w * 32 + byte * 8 + i;
+}
+
+} // namespace v224

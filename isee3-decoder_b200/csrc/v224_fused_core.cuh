@@ -1,0 +1,184 @@
+// v224_fused_core.cuh -- arithmetic core of the fused 8-stage ACS pass.
+//
+// Index algebra (not in the reference; it follows from the butterfly's rotate-left index map,
+// viterbi224_sse2.c:296-299,326-327: old {b, b+2^22} -> new {2b, 2b+1}):
+//
+//   Keep every value in a fixed "slot" p (23 bits) for the whole pass.  If slot p holds state
+//   rotl^t(p) after t stages, stage t+1 pairs the slots that differ in slot bit 22-t, and the
+//   survivor for input bit 0 / 1 stays in the slot whose bit 22-t is 0 / 1.  An 8-stage pass
+//   therefore only ever combines slots that differ in slot bits 22..15 ("m", 8 bits); slot bits
+//   14..0 ("j") never mix.  A tile is all 256 m x 64 consecutive j.  Stages 1-4 butterfly
+//   over m's high nibble mh (a thread holds the 16 mh rows of one ml), stages 5-8 over the low
+//   nibble ml (a thread holds the 16 ml rows of one mh); the two rounds exchange through shared
+//   memory once.  After 8 stages slot (m, j) holds state (j << 8) | m.
+//
+//   Two columns j, j+1 share one 32-bit register (packed 16-bit metrics); both halves run the
+//   same butterfly with their own branch metric.
+//
+// Branch metrics: for the butterfly whose bit-0 member sits in slot p (stage bit cleared) the
+// expected symbols are parity(reg24 & POLYn) with reg24 = rotl^(t-1)(p) << 1 (viterbi224_sse2.c
+// :74-77 evaluates the same parity into Branchtab224).  Parity is linear, so it splits into a
+// per-thread part and a compile-time per-register part; per stage a thread needs only four
+// packed (x) and four packed (0x8000 - delta) operands.
+//
+// This header is also compiled for the host by tests/emu (V224_HOST_EMU) to check the index
+// algebra against the CPU oracle without a GPU; the product only uses the device path.
+#pragma once
+#include "v224_common.cuh"
+
+#if defined(V224_HOST_EMU) && !defined(__CUDA_ARCH__)
+#define V224_HD
+namespace v224 {
+static inline uint32_t f_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+static inline uint32_t f_addmin_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t lo = ((a & 0xffff) + (b & 0xffff)) & 0xffff, hi = ((a >> 16) + (b >> 16)) & 0xffff;
+    uint32_t clo = c & 0xffff, chi = c >> 16;
+    return (lo < clo ? lo : clo) | ((hi < chi ? hi : chi) << 16);
+}
+static inline uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t n = (sel >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t)(pool >> (8 * (n & 7))) & 0xff;
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline uint32_t f_minu2(uint32_t a, uint32_t b)
+{
+    uint32_t lo = (a & 0xffff) < (b & 0xffff) ? (a & 0xffff) : (b & 0xffff);
+    uint32_t hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+static inline uint32_t f_maxu2(uint32_t a, uint32_t b)
+{
+    uint32_t lo = (a & 0xffff) > (b & 0xffff) ? (a & 0xffff) : (b & 0xffff);
+    uint32_t hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+}
+#else
+#define V224_HD __device__ __forceinline__
+namespace v224 {
+V224_HD uint32_t f_popc(uint32_t x) { return (uint32_t)__popc(x); }
+V224_HD uint32_t f_addmin_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }   // VIADDMNMX.U16x2
+V224_HD uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }             // PRMT
+V224_HD uint32_t f_minu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }                                   // VIMNMX.U16x2
+V224_HD uint32_t f_maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+}
+#endif
+
+namespace v224 {
+
+// Slot-bit mask of POLY at stage t (1-based): slot bit s feeds register bit ((s+t-1) mod 23)+1.
+__host__ __device__ constexpr uint32_t slotmask(uint32_t poly, int t)
+{
+    uint32_t m = 0;
+    for (int s = 0; s < 23; s++)
+        if ((poly >> (((s + t - 1) % 23) + 1)) & 1u) m |= 1u << s;
+    return m;
+}
+
+// label = e1 | e2 << 1 of the linear (un-flipped) part
+template <int T> V224_HD uint32_t slot_label(uint32_t p)
+{
+    constexpr uint32_t m1 = slotmask(POLY1, T), m2 = slotmask(POLY2, T);
+    return (f_popc(p & m1) & 1u) | ((f_popc(p & m2) & 1u) << 1);
+}
+constexpr uint32_t FLIP_LABEL = (uint32_t)G1FLIP | ((uint32_t)G2FLIP << 1);
+
+// Operand table in shared memory: optab[(t-1)*32 + beta*8 + {0..3: X[beta^i], 4..7: K[beta^i]}]
+constexpr int OPTAB_WORDS = FK * 32;
+
+// Entry `e` (0 .. FK*32) of the operand table for the pass whose symbols are sym[2*(t-1)], sym[2*(t-1)+1].
+template <typename SymPtr>
+V224_HD uint32_t optab_entry(int e, SymPtr sym)
+{
+    const int t = e / 32 + 1, beta = (e / 8) & 3, isK = (e / 4) & 1, i = e & 3;
+    const int s0 = sym[2 * (t - 1)], s1 = sym[2 * (t - 1) + 1];
+    // label of slot bit 0 (the upper half's extra label) at stage t
+    uint32_t m1 = slotmask(POLY1, t), m2 = slotmask(POLY2, t);
+    const uint32_t hc = (m1 & 1u) | ((m2 & 1u) << 1);
+    const uint32_t l_lo = (uint32_t)(beta ^ i), l_hi = l_lo ^ hc;
+    // (BT0 ^ s0) + (BT1 ^ s1), viterbi224_sse2.c:292
+    const int x_lo = ((l_lo & 1) ? 255 - s0 : s0) + ((l_lo & 2) ? 255 - s1 : s1);
+    const int x_hi = ((l_hi & 1) ? 255 - s0 : s0) + ((l_hi & 2) ? 255 - s1 : s1);
+    if (!isK) return (uint32_t)x_lo | ((uint32_t)x_hi << 16);
+    const int d_lo = 2 * x_lo - 510, d_hi = 2 * x_hi - 510;     // x - (510 - x), :293
+    return (uint32_t)(0x8000 - d_lo) | ((uint32_t)(0x8000 - d_hi) << 16);
+}
+
+// One trellis stage over a thread's 16 rows x 4 packed registers.
+//   A[inner][q]  : packed P metrics, halves = columns 2q, 2q+1 of the thread's 8 columns
+//   pbase        : the thread's slot bits outside (inner, q, h)
+//   optab        : shared operand table
+//   dw[4]        : returns the 128 decision bits of this thread/stage in fused layout
+template <int T>
+V224_HD void acs_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t (&dw)[4])
+{
+    constexpr int sb = FR - 1 - ((T - 1) % FR);          // stage bit inside `inner`
+    constexpr int ishift = (T <= FR) ? 19 : 15;           // slot position of `inner`
+    const uint32_t beta = slot_label<T>(pbase) ^ FLIP_LABEL;
+    const uint32_t *tab = optab + (T - 1) * 32 + beta * 8;
+    uint32_t Xv[4], Kv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { Xv[i] = tab[i]; Kv[i] = tab[4 + i]; }
+    dw[0] = dw[1] = dw[2] = dw[3] = 0;
+#pragma unroll
+    for (int ia = 0; ia < 16; ia++) {
+        if ((ia >> sb) & 1) continue;
+        const int ic = ia | (1 << sb);
+        uint32_t D0[4], D1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t off = ((uint32_t)ia << ishift) | ((uint32_t)q << 1);
+            const uint32_t c = slot_label<T>(off);
+            const uint32_t X = Xv[c], Y = Xv[c ^ 3], K0 = Kv[c], K1 = Kv[c ^ 3];
+            const uint32_t a = A[ia][q], cc = A[ic][q];
+            // m0 = a+x, m1 = c+y, m2 = a+y, m3 = c+x          (viterbi224_sse2.c:296-299)
+            const uint32_t t0 = cc + Y, t1 = cc + X;
+            // decision0 = m0 > m1  <=>  (c - a) - delta < 0  <=> bit15 of D0 clear   (:316)
+            // decision1 = m2 > m3  <=>  (c - a) + delta < 0  <=> bit15 of D1 clear   (:317)
+            D0[q] = cc - a + K0;
+            D1[q] = cc - a + K1;
+            A[ia][q] = f_addmin_u16x2(a, X, t0);          // min(m0, m1) -> state 2b    (:319)
+            A[ic][q] = f_addmin_u16x2(a, Y, t1);          // min(m2, m3) -> state 2b+1  (:320)
+        }
+        // gather the (inverted) sign bits: byte = (q&1)*2 + half, bit-in-byte = (inner&3)*2 + q/2
+#pragma unroll
+        for (int qq = 0; qq < 2; qq++) {
+            const uint32_t s0 = f_prmt(D0[2 * qq], D0[2 * qq + 1], 0xfdb9);
+            const uint32_t s1 = f_prmt(D1[2 * qq], D1[2 * qq + 1], 0xfdb9);
+            dw[ia >> 2] = (~s0 & (0x01010101u << (((ia & 3) << 1) | qq))) | dw[ia >> 2];
+            dw[ic >> 2] = (~s1 & (0x01010101u << (((ic & 3) << 1) | qq))) | dw[ic >> 2];
+        }
+    }
+}
+
+// packed min / max over a thread's 64 registers
+V224_HD uint32_t tile_min(const uint32_t (&A)[16][4])
+{
+    uint32_t m = A[0][0];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) m = f_minu2(m, A[i][q]);
+    uint32_t lo = m & 0xffff, hi = m >> 16;
+    return lo < hi ? lo : hi;
+}
+V224_HD uint32_t tile_max(const uint32_t (&A)[16][4])
+{
+    uint32_t m = A[0][0];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) m = f_maxu2(m, A[i][q]);
+    uint32_t lo = m & 0xffff, hi = m >> 16;
+    return lo > hi ? lo : hi;
+}
+
+} // namespace v224

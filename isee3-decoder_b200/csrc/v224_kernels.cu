@@ -1,0 +1,567 @@
+// v224_kernels.cu -- sm_100a kernels of the B200 viterbi224 decoder.
+//
+//   k_init            metric fill + control-block reset               (viterbi224_sse2.c:37-53)
+//   k_acs_fused       8 trellis stages per HBM pass                   (viterbi224_sse2.c:264-328, x8)
+//   k_acs_single      1 trellis stage; SAT variant = exact int16-saturating arithmetic
+//   k_chainback_*     frame traceback, speculative segments + verify  (viterbi224_sse2.c:113-161)
+//   k_walk            decodebit / decodeword walk                     (viterbi224_sse2.c:164-243)
+//   k_stream_trace    one walk per output bit (vdecode.c:145-152 pattern, batched)
+//   k_argmin, k_minmax, k_export_row, k_export_metrics, k_import_metrics
+//
+// Renormalisation (viterbi224_sse2.c:351-377) never touches HBM: the last CTA of every pass
+// ("resolver") replays the reference's test on state 0 and folds the adjustment into the
+// 64-bit offset Ctl::O (R_reference = P_hbm + O).
+#include "v224_common.cuh"
+#include "v224_fused_core.cuh"
+#include "v224_kernels.h"
+
+namespace v224 {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_cs_v4(void *p, uint4 v)   // streaming store: decision rows are write-once
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_v8(void *p, const uint32_t (&v)[8])   // 256-bit store (sm_100+)
+{
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+// Reset the per-pass statistics (resolver, and k_init).
+__device__ __forceinline__ void reset_stats(Ctl *c)
+{
+#pragma unroll
+    for (int t = 0; t <= FK; t++) { c->s0[t] = 0; c->minP[t] = 0xffffffffu; }
+    c->maxP_end = 0;
+    c->ticket = 0;
+}
+
+// The resolver: executed by ONE thread after every CTA of a pass has published its statistics.
+// Replays viterbi224_sse2.c:351-377 for each of the pass's `ks` stages on the virtual
+// reference metric R = P + O, then prepares the next pass (sub, R0, maxR) and advances T/pos.
+__device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
+{
+    long long O = sat ? -32768ll : c->O;      // a SAT stage stores P = R + 32768
+    for (int t = 1; t <= ks; t++) {
+        const long long R0 = (long long)c->s0[t] + O;
+        if (R0 >= RENORM_TRIGGER) {                                   // :351 state 0 only
+            if (!(careful || t == ks) || c->minP[t] == 0xffffffffu) { c->error |= 1; break; }
+            const long long minR = (long long)c->minP[t] + O;         // :358-366 global minimum
+            // :354,:366 the minimum is read through a uint16_t: a negative one counts 65536 more
+            const long long adjust = (minR < 0 ? minR + 65536 : minR) + 32768;
+            c->renormals += adjust;                                   // :367
+            c->renorm_count += 1;
+            O -= minR + 32768;                                        // :373 (mod 2^16 == this, min -> SHRT_MIN)
+        }
+    }
+    const unsigned mn = c->minP[ks], mx = c->maxP_end, z = c->s0[ks];
+    if (mn == 0xffffffffu || mx < mn) c->error |= 2;
+    O += mn;                         // the next pass subtracts mn from every P while loading
+    c->sub = (int)mn;
+    c->O = O;
+    c->R0 = (long long)z - mn + O;
+    c->maxR = (long long)mx - mn + O;
+    c->T += ks;
+    c->pos += ks;
+    c->cur ^= 1;
+    reset_stats(c);
+}
+
+// ------------------------------------------------------------------------------------------
+// init
+// ------------------------------------------------------------------------------------------
+// P = bias everywhere, 0 in the start state, O = SHRT_MIN  <=>  R = SHRT_MIN+bias / SHRT_MIN.
+__global__ void __launch_bounds__(256) k_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;     // one uint4 (8 metrics) per thread
+    const uint32_t b = (uint32_t)bias | ((uint32_t)bias << 16);
+    uint4 v = make_uint4(b, b, b, b);
+    reinterpret_cast<uint4 *>(m0)[i] = v;
+    __syncthreads();
+    if (start_state / 8 == i && start_value >= 0) m0[start_state] = (uint16_t)start_value;
+    if (i == 0) {
+        c->O = -32768;
+        c->renormals = 0;
+        c->T = 0;
+        c->pos = 0;
+        c->renorm_count = 0;
+        c->sub = 0;
+        c->R0 = (start_state == 0 && start_value >= 0 ? start_value : bias) - 32768;
+        c->maxR = bias - 32768;
+        c->cur = 0;
+        c->error = 0;
+        reset_stats(c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused 8-stage pass
+// ------------------------------------------------------------------------------------------
+struct __align__(16) FusedSmem {
+    uint32_t tile[256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 = 32 KiB
+    uint32_t optab[OPTAB_WORDS];                 // 1 KiB
+};
+
+template <int T>
+__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, const FusedArgs &a,
+                                            Ctl *c, long long T0, bool careful, uint32_t chunk)
+{
+    uint32_t dw[4];
+    acs_stage<T>(A, pbase, optab, dw);
+    const long long row = (T0 + T - 1) % a.len;
+    st_cs_v4(reinterpret_cast<uint8_t *>(a.ring) + (size_t)row * ROWBYTES + (size_t)chunk * 16, make_uint4(dw[0], dw[1], dw[2], dw[3]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c->s0[T] = A[0][0] & 0xffffu;            // slot 0 always holds state 0
+        a.row_fmt[row] = (uint8_t)T;
+    }
+    if (careful && T < FK) {
+        uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
+        if ((threadIdx.x & 31) == 0) atomicMin(&c->minP[T], mn);
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    Ctl *c = a.ctl;
+
+    // Every CTA takes the same go / no-go decision from the (quiescent) control block.
+    if (c->pos != a.expected_pos || c->error) return;
+    if (c->maxR + 510ll * FK > 32767) return;                      // reference could saturate: host runs SAT stages
+    const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
+    const long long T0 = c->T;
+    const uint32_t sub = (uint32_t)c->sub * 0x10001u;
+    const uint16_t *oldm = a.metrics[c->cur];
+    uint16_t *newm = a.metrics[c->cur ^ 1];
+
+    const uint32_t tid = threadIdx.x, tau = blockIdx.x;
+    const uint32_t thr = tid >> 3, g = tid & 7;                    // row group, column group
+    const uint32_t chunk = tau * FUSED_THREADS + tid;
+
+    // operand table for the 8 symbol pairs of this pass
+    const uint8_t *sym = a.syms + 2 * (size_t)a.expected_pos;
+    for (int e = tid; e < OPTAB_WORDS; e += FUSED_THREADS) sm.optab[e] = optab_entry(e, sym);
+
+    // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 8 columns ----
+    uint32_t A[16][4];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(oldm) + ((size_t)thr * 32768 + tau * FUSED_TILE_COLS + g * 8) / 8;
+#pragma unroll
+        for (int mh = 0; mh < 16; mh++) {
+            const uint4 v = src[(size_t)mh * 16 * 32768 / 8];
+            A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][2] = v.z - sub; A[mh][3] = v.w - sub;
+        }
+    }
+    __syncthreads();                                               // optab ready
+    {
+        const uint32_t pbase = (thr << 15) | (tau << 6) | (g << 3);
+        fused_stage<1>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<2>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<3>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<4>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+    }
+    // ---- exchange: rows m = mh*16 + ml, 128 B per row ----
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(sm.tile);
+#pragma unroll
+        for (int mh = 0; mh < 16; mh++) t4[(mh * 16 + thr) * 8 + g] = make_uint4(A[mh][0], A[mh][1], A[mh][2], A[mh][3]);
+        __syncthreads();
+#pragma unroll
+        for (int ml = 0; ml < 16; ml++) {
+            const uint4 v = t4[(thr * 16 + ml) * 8 + g];
+            A[ml][0] = v.x; A[ml][1] = v.y; A[ml][2] = v.z; A[ml][3] = v.w;
+        }
+    }
+    // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
+    {
+        const uint32_t pbase = (thr << 19) | (tau << 6) | (g << 3);
+        fused_stage<5>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<6>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<7>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<8>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+    }
+    // ---- statistics of the final stage ----
+    {
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
+        if ((tid & 31) == 0) { atomicMin(&c->minP[FK], mn); atomicMax(&c->maxP_end, mx); }
+    }
+    // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B ----
+    {
+        const uint32_t jbase = tau * FUSED_TILE_COLS + g * 8;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) w[i] = __byte_perm(A[2 * i][q], A[2 * i + 1][q], h ? 0x7632 : 0x5410);
+                st_v8(newm + ((size_t)(jbase + q * 2 + h) << 8) + thr * 16, w);
+            }
+        }
+    }
+    // ---- last CTA resolves the pass ----
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&c->ticket, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1 && tid == 0) {
+        __threadfence();
+        if (careful) c->n_careful++;
+        c->n_fused++;
+        resolve_pass(c, FK, careful, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// single stage (remainders, per-bit streaming, exact saturating fallback)
+// ------------------------------------------------------------------------------------------
+// One thread = 8 butterflies b0..b0+7 -> 16 new states 2*b0 .. 2*b0+15 (canonical row layout).
+template <bool SAT>
+__global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
+{
+    Ctl *c = a.ctl;
+    if (c->pos != a.expected_pos || c->error) return;
+    if (!SAT && c->maxR + 510 > 32767) return;                     // reference could saturate: use the SAT variant
+    const long long T0 = c->T;
+    const int sub = c->sub;
+    const long long O = c->O;
+    const uint16_t *oldm = a.metrics[c->cur];
+    uint16_t *newm = a.metrics[c->cur ^ 1];
+    const int s0 = a.use_arg_syms ? a.sym0 : a.syms[2 * (size_t)a.expected_pos];
+    const int s1 = a.use_arg_syms ? a.sym1 : a.syms[2 * (size_t)a.expected_pos + 1];
+
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b0 = gid * 8;
+    const uint4 va = reinterpret_cast<const uint4 *>(oldm)[gid];
+    const uint4 vc = reinterpret_cast<const uint4 *>(oldm)[gid + NBFLY / 8];
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+    uint32_t out[8];
+    uint32_t dec = 0;
+    int mn = 0x7fffffff, mx = -0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const uint32_t b = b0 + e;
+        // expected symbols, viterbi224_sse2.c:75-76
+        const int e1 = G1FLIP ^ (__popc((2u * b) & POLY1) & 1);
+        const int e2 = G2FLIP ^ (__popc((2u * b) & POLY2) & 1);
+        const int x = (e1 ? 255 - s0 : s0) + (e2 ? 255 - s1 : s1);     // :292
+        const int y = 510 - x;                                        // :293
+        int pa = (int)((wa[e >> 1] >> ((e & 1) * 16)) & 0xffff) - sub;
+        int pc = (int)((wc[e >> 1] >> ((e & 1) * 16)) & 0xffff) - sub;
+        int m0, m1, m2, m3;
+        if (SAT) {
+            // exact reference arithmetic on R = P + O (int16, saturating adds, :296-299)
+            const int ra = (int)(pa + O), rc = (int)(pc + O);
+            m0 = min(ra + x, 32767); m1 = min(rc + y, 32767);
+            m2 = min(ra + y, 32767); m3 = min(rc + x, 32767);
+        } else {
+            m0 = pa + x; m1 = pc + y; m2 = pa + y; m3 = pc + x;
+        }
+        const int d0 = m0 > m1, d1 = m2 > m3;                         // :316-317 strict
+        int n0 = min(m0, m1), n1 = min(m2, m3);                       // :319-320
+        if (SAT) { n0 += 32768; n1 += 32768; }                        // store P = R + 32768
+        dec |= (uint32_t)d0 << (2 * e) | (uint32_t)d1 << (2 * e + 1); // :324
+        out[e] = (uint32_t)n0 | ((uint32_t)n1 << 16);                 // :326-327 states 2b, 2b+1
+        mn = min(mn, min(n0, n1));
+        mx = max(mx, max(n0, n1));
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(newm) + (size_t)gid * 2;
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    const long long row = T0 % a.len;
+    // 16 decision bits per thread; pair lanes into 32-bit words
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, dec, 1);
+    if ((threadIdx.x & 1) == 0)
+        __stcs(a.ring + (size_t)row * ROWWORDS + gid / 2, dec | (other << 16));
+
+    const uint32_t wmn = __reduce_min_sync(0xffffffffu, (uint32_t)mn);
+    const uint32_t wmx = __reduce_max_sync(0xffffffffu, (uint32_t)mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&c->minP[1], wmn); atomicMax(&c->maxP_end, wmx); }
+    if (gid == 0) { c->s0[1] = out[0] & 0xffffu; a.row_fmt[row] = ROWFMT_CANON; }
+
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&c->ticket, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) {
+        __threadfence();
+        if (SAT) c->n_sat++; else c->n_single++;
+        resolve_pass(c, 1, true, SAT);
+    }
+}
+template __global__ void k_acs_single<false>(SingleArgs);
+template __global__ void k_acs_single<true>(SingleArgs);
+
+// ------------------------------------------------------------------------------------------
+// traceback
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t read_decision(const uint32_t *ring, const uint8_t *row_fmt, long long row, uint32_t state)
+{
+    const uint8_t f = row_fmt[row];
+    const uint32_t bit = f == ROWFMT_CANON ? state : fused_bit_address(f, state);
+    return (ring[(size_t)row * ROWWORDS + (bit >> 5)] >> (bit & 31)) & 1u;     // viterbi224_sse2.c:141
+}
+
+// Speculative segment walk.  Segment i covers bits [i*L, min((i+1)*L, nbits)).  Its end state is
+// guessed by walking `warm` extra stages back from state 0 (the true endstate for the last one).
+__global__ void k_chainback_seg(TraceArgs a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out,
+                                uint32_t *seg_guess, uint32_t *seg_final)
+{
+    const uint32_t nseg = (nbits + L - 1) / L;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    const uint32_t lo = i * L, hi = min(nbits, (i + 1) * L);
+    uint32_t st;
+    if (hi == nbits) {
+        st = endstate & STATEMASK;
+    } else {
+        uint32_t w = min(nbits, hi + (uint32_t)warm);
+        st = (w == nbits) ? (endstate & STATEMASK) : 0u;
+        while (w > hi) {
+            --w;
+            const uint32_t bit = read_decision(a.ring, a.row_fmt, w % (uint32_t)a.len, st);
+            st = (bit << (K - 2)) | (st >> 1);
+        }
+    }
+    seg_guess[i] = st;
+    uint32_t n = hi;
+    uint32_t dbyte = 0;
+    while (n > lo) {
+        --n;
+        dbyte = ((st & 1u) << 7) | (dbyte >> 1);                              // :137
+        if ((n & 7) == 0) out[n >> 3] = (uint8_t)dbyte;                       // :138-139
+        const uint32_t bit = read_decision(a.ring, a.row_fmt, n % (uint32_t)a.len, st);   // :140-141
+        st = (bit << (K - 2)) | (st >> 1);                                    // :142
+    }
+    seg_final[i] = st;
+}
+
+// Verify the guesses from the last segment backwards; re-walk a segment serially when its guess
+// was wrong.  Result: `out` equals the reference's serial chainback bit for bit.
+__global__ void k_chainback_fix(TraceArgs a, uint32_t nbits, int L, uint8_t *out, uint32_t *seg_guess, uint32_t *seg_final,
+                                unsigned *redo_count)
+{
+    const uint32_t nseg = (nbits + L - 1) / L;
+    if (nseg < 2) return;
+    for (int i = (int)nseg - 2; i >= 0; i--) {
+        const uint32_t truth = seg_final[i + 1];
+        if (seg_guess[i] == truth) continue;
+        atomicAdd(redo_count, 1u);
+        const uint32_t lo = (uint32_t)i * L, hi = (uint32_t)(i + 1) * L;
+        uint32_t st = truth, n = hi, dbyte = 0;
+        while (n > lo) {
+            --n;
+            dbyte = ((st & 1u) << 7) | (dbyte >> 1);
+            if ((n & 7) == 0) out[n >> 3] = (uint8_t)dbyte;
+            const uint32_t bit = read_decision(a.ring, a.row_fmt, n % (uint32_t)a.len, st);
+            st = (bit << (K - 2)) | (st >> 1);
+        }
+        seg_guess[i] = truth;
+        seg_final[i] = st;
+    }
+}
+
+// decodebit / decodeword: walk `delay` rows back from ring position dp (viterbi224_sse2.c:164-243).
+// result[0] = last bit (or -1), result[1..2] = the 64-bit shift register of decodeword.
+__global__ void k_walk(TraceArgs a, long long dp, int delay, uint32_t endstate, int use_argmin, const unsigned long long *argmin_key,
+                       unsigned long long *result)
+{
+    uint32_t st = use_argmin ? (uint32_t)(*argmin_key & 0xffffffffu) : endstate;
+    st &= STATEMASK;
+    long long row = dp;
+    int bit = -1;
+    unsigned long long word = 0;
+    while (delay-- > 0) {
+        if (--row < 0) row = a.len - 1;                                        // :190-191
+        bit = (int)read_decision(a.ring, a.row_fmt, row, st);
+        st = ((uint32_t)bit << (K - 2)) | (st >> 1);
+        word = ((unsigned long long)bit << 63) | (word >> 1);                  // :237
+    }
+    result[0] = (unsigned long long)(long long)bit;
+    result[1] = word;
+}
+
+// Batched streaming traceback: output i is what decodebit(delay, 0) returns right after stage
+// T_first + i has been appended (vdecode.c:145-152).  Rows older than the last init read as 0.
+__global__ void k_stream_trace(TraceArgs a, long long T_first, int nout, int delay, uint8_t *bits_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nout) return;
+    long long t = T_first + i + 1;          // stages appended so far; newest row = t-1
+    uint32_t st = 0;
+    uint32_t bit = 0;
+    for (int s = 0; s < delay; s++) {
+        --t;
+        if (t < 0) { bit = 0; break; }
+        bit = read_decision(a.ring, a.row_fmt, t % a.len, st);
+        st = (bit << (K - 2)) | (st >> 1);
+    }
+    bits_out[i] = (uint8_t)bit;
+}
+
+// ------------------------------------------------------------------------------------------
+// reductions / export
+// ------------------------------------------------------------------------------------------
+// argmin with lowest index on ties (viterbi224_sse2.c:173-182): key = (P << 32) | index.
+__global__ void __launch_bounds__(256) k_argmin(const uint16_t *m, unsigned long long *key)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 v = reinterpret_cast<const uint4 *>(m)[gid];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const unsigned long long p = (w[e >> 1] >> ((e & 1) * 16)) & 0xffff;
+        const unsigned long long k = (p << 32) | (gid * 8 + e);
+        best = k < best ? k : best;
+    }
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(key, best);
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const uint16_t *m, unsigned *mnmx)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 v = reinterpret_cast<const uint4 *>(m)[gid];
+    uint32_t lo = __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w));
+    uint32_t hi = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+    uint32_t mn = min(lo & 0xffff, lo >> 16), mx = max(hi & 0xffff, hi >> 16);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mnmx[0], mn); atomicMax(&mnmx[1], mx); }
+}
+
+// Test hook: one decision row in the reference's canonical layout.
+__global__ void __launch_bounds__(256) k_export_row(TraceArgs a, long long row, uint32_t *out)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;     // output word
+    const uint8_t f = a.row_fmt[row];
+    const uint32_t *r = a.ring + (size_t)row * ROWWORDS;
+    if (f == ROWFMT_CANON) { out[w] = r[w]; return; }
+    uint32_t v = 0;
+    for (int b = 0; b < 32; b++) {
+        const uint32_t addr = fused_bit_address(f, w * 32 + b);
+        v |= ((r[addr >> 5] >> (addr & 31)) & 1u) << b;
+    }
+    out[w] = v;
+}
+
+// Test hooks: metrics in the reference's int16 domain (R = P - sub + O) and back.
+__global__ void __launch_bounds__(256) k_export_metrics(const uint16_t *m, const Ctl *c, int16_t *out, int *range_error)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = (long long)m[i] - c->sub + c->O;
+    if (r < -32768 || r > 32767) *range_error = 1;
+    out[i] = (int16_t)r;
+}
+__global__ void __launch_bounds__(256) k_import_metrics(uint16_t *m, const int16_t *in)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    m[i] = (uint16_t)((int)in[i] + 32768);
+}
+// after k_import_metrics + k_minmax: make the control block describe the imported state
+__global__ void k_import_ctl(Ctl *c, const uint16_t *m, const unsigned *mnmx, long long renormals, long long T)
+{
+    c->O = -32768;
+    c->sub = 0;
+    c->renormals = renormals;
+    c->T = T;
+    c->R0 = (long long)m[0] - 32768;
+    c->maxR = (long long)mnmx[1] - 32768;
+    c->error = 0;
+    reset_stats(c);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers (called from the runtime; all asynchronous on `st`)
+// ------------------------------------------------------------------------------------------
+static bool g_fused_attr_set[64];
+cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st)
+{
+    k_init<<<NSTATES / 8 / 256, 256, 0, st>>>(m0, c, start_state, bias, start_value);
+    return cudaGetLastError();
+}
+cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !g_fused_attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_acs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        g_fused_attr_set[dev] = true;
+    }
+    k_acs_fused<<<FUSED_TILES, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)
+{
+    if (sat) k_acs_single<true><<<NBFLY / 8 / 256, 256, 0, st>>>(a);
+    else     k_acs_single<false><<<NBFLY / 8 / 256, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
+                             uint32_t *seg_final, unsigned *redo_count, cudaStream_t st)
+{
+    const uint32_t nseg = (nbits + L - 1) / L;
+    k_chainback_seg<<<(nseg + 31) / 32, 32, 0, st>>>(a, nbits, endstate, L, warm, out, seg_guess, seg_final);
+    k_chainback_fix<<<1, 1, 0, st>>>(a, nbits, L, out, seg_guess, seg_final, redo_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t endstate, int use_argmin, const unsigned long long *argmin_key,
+                        unsigned long long *result, cudaStream_t st)
+{
+    k_walk<<<1, 1, 0, st>>>(a, dp, delay, endstate, use_argmin, argmin_key, result);
+    return cudaGetLastError();
+}
+cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st)
+{
+    if (nout <= 0) return cudaSuccess;
+    k_stream_trace<<<(nout + 63) / 64, 64, 0, st>>>(a, T_first, nout, delay, bits_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(key, 0xff, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    k_argmin<<<NSTATES / 8 / 256, 256, 0, st>>>(m, key);
+    return cudaGetLastError();
+}
+cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st)
+{
+    const unsigned init[2] = {0xffffffffu, 0u};
+    cudaError_t e = cudaMemcpyAsync(mnmx, init, sizeof init, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_minmax<<<NSTATES / 8 / 256, 256, 0, st>>>(m, mnmx);
+    return cudaGetLastError();
+}
+cudaError_t launch_export_row(const TraceArgs &a, long long row, uint32_t *out, cudaStream_t st)
+{
+    k_export_row<<<ROWWORDS / 256, 256, 0, st>>>(a, row, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_export_metrics(const uint16_t *m, const Ctl *c, int16_t *out, int *range_error, cudaStream_t st)
+{
+    k_export_metrics<<<NSTATES / 256, 256, 0, st>>>(m, c, out, range_error);
+    return cudaGetLastError();
+}
+cudaError_t launch_import_metrics(uint16_t *m, const int16_t *in, Ctl *c, unsigned *mnmx, long long renormals, long long T, cudaStream_t st)
+{
+    k_import_metrics<<<NSTATES / 256, 256, 0, st>>>(m, in);
+    cudaError_t e = launch_minmax(m, mnmx, st);
+    if (e != cudaSuccess) return e;
+    k_import_ctl<<<1, 1, 0, st>>>(c, m, mnmx, renormals, T);
+    return cudaGetLastError();
+}
+
+} // namespace v224

@@ -1,0 +1,50 @@
+// v224_kernels.h -- launch interface between the host runtime and the CUDA kernels.
+#pragma once
+#include "v224_common.cuh"
+
+namespace v224 {
+
+struct FusedArgs {
+    Ctl *ctl;
+    uint16_t *metrics[2];
+    uint32_t *ring;
+    uint8_t *row_fmt;
+    const uint8_t *syms;     // device symbols of the running update call (2 per bit)
+    int len;                 // ring rows
+    int expected_pos;        // stages of this call that must already be done
+    int force_careful;       // test knob: record per-stage minima regardless
+};
+
+struct SingleArgs {
+    Ctl *ctl;
+    uint16_t *metrics[2];
+    uint32_t *ring;
+    uint8_t *row_fmt;
+    const uint8_t *syms;
+    int len;
+    int expected_pos;
+    int use_arg_syms;        // per-bit streaming: the two symbols travel as kernel arguments
+    int sym0, sym1;
+};
+
+struct TraceArgs {
+    const uint32_t *ring;
+    const uint8_t *row_fmt;
+    int len;
+};
+
+cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
+cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
+cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
+cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
+                             uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);
+cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t endstate, int use_argmin, const unsigned long long *argmin_key,
+                        unsigned long long *result, cudaStream_t st);
+cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st);
+cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st);
+cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st);
+cudaError_t launch_export_row(const TraceArgs &a, long long row, uint32_t *out, cudaStream_t st);
+cudaError_t launch_export_metrics(const uint16_t *m, const Ctl *c, int16_t *out, int *range_error, cudaStream_t st);
+cudaError_t launch_import_metrics(uint16_t *m, const int16_t *in, Ctl *c, unsigned *mnmx, long long renormals, long long T, cudaStream_t st);
+
+} // namespace v224

@@ -1,0 +1,629 @@
+// v224_runtime.cu -- host runtime and C ABI of libviterbi224_b200.
+//
+// Exports exactly the nine symbols of the reference's viterbi224.h:8-16 (see
+// include/viterbi224.h) plus the v224x_* extensions (include/viterbi224_b200.h).
+// Everything that touches a metric or a decision bit runs in the CUDA kernels of
+// v224_kernels.cu; there is no CPU arithmetic path in this file.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include "v224_kernels.h"
+#include "../../include/viterbi224.h"
+#include "../../include/viterbi224_b200.h"
+
+using namespace v224;
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_device = -1;      // -1: leave the CUDA current device alone (device 0 by default)
+
+void set_err(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    if (getenv("V224_DEBUG")) fprintf(stderr, "[viterbi224_b200] %s\n", g_err);
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+// ---- pooled ring allocations: callers such as decode.c:216-229 create and delete a 1 GiB
+// decoder per frame; keep the last few rings around instead of going back to the driver. ----
+struct PoolEntry { int dev; size_t bytes; void *ptr; };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+constexpr size_t POOL_MAX_ENTRIES = 4;
+
+void *pool_get(int dev, size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i].dev == dev && g_pool[i].bytes == bytes) {
+                void *p = g_pool[i].ptr;
+                g_pool.erase(g_pool.begin() + i);
+                return p;
+            }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        // release cached rings and retry once
+        std::vector<PoolEntry> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            drop.swap(g_pool);
+        }
+        for (auto &e : drop) cudaFree(e.ptr);
+        cudaGetLastError();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    return p;
+}
+void pool_put(int dev, size_t bytes, void *ptr)
+{
+    void *evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool.push_back({dev, bytes, ptr});
+        if (g_pool.size() > POOL_MAX_ENTRIES) { evict = g_pool.front().ptr; g_pool.erase(g_pool.begin()); }
+    }
+    if (evict) cudaFree(evict);
+}
+
+struct Decoder {
+    uint32_t magic;
+    int dev;
+    int len;
+    cudaStream_t stream;
+    uint16_t *metrics[2];
+    uint32_t *ring;
+    size_t ring_bytes;
+    uint8_t *row_fmt;
+    Ctl *ctl;
+    Ctl *h_ctl;                 // pinned mirror, refreshed at the end of every update
+    uint8_t *dsyms; size_t dsyms_cap;
+    uint8_t *dout;  size_t dout_cap;       // chainback / stream output staging
+    uint32_t *seg;  size_t seg_cap;        // chainback segment bookkeeping
+    unsigned *d_redo;
+    unsigned long long *d_key;             // argmin key
+    unsigned *d_mnmx;
+    unsigned long long *d_result, *h_result;   // walk results (pinned host copy)
+    int *d_flag;
+    cudaEvent_t ev0, ev1, kev0, kev1;
+    // options
+    int force_single, force_sat, force_careful, chain_seg, chain_warm;
+    // counters
+    unsigned long long launches, acs_launches_timed, chainback_redo;
+    double acs_ms;
+    int time_kernels;
+};
+constexpr uint32_t MAGIC = 0x56323234u;   // "V224"
+
+Decoder *as_dec(void *p)
+{
+    Decoder *d = static_cast<Decoder *>(p);
+    if (!d) return nullptr;
+    if (d->magic != MAGIC) { set_err("not a viterbi224_b200 handle"); return nullptr; }
+    return d;
+}
+
+int bind(Decoder *d)
+{
+    CU(cudaSetDevice(d->dev));
+    return 0;
+}
+
+int grow(void **buf, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    size_t n = std::max(need, (size_t)4096);
+    CU(cudaMalloc(buf, n));
+    *cap = n;
+    return 0;
+}
+
+int sync_ctl(Decoder *d)
+{
+    CU(cudaMemcpyAsync(d->h_ctl, d->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->h_ctl->error) { set_err("device control block reports invariant violation %d", d->h_ctl->error); return -1; }
+    return 0;
+}
+
+void destroy(Decoder *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->dev);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
+    cudaFree(d->metrics[0]); cudaFree(d->metrics[1]); cudaFree(d->row_fmt); cudaFree(d->ctl);
+    cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
+    cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag);
+    if (d->h_ctl) cudaFreeHost(d->h_ctl);
+    if (d->h_result) cudaFreeHost(d->h_result);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->kev0) cudaEventDestroy(d->kev0);
+    if (d->kev1) cudaEventDestroy(d->kev1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    d->magic = 0;
+    cudaGetLastError();
+    free(d);
+}
+
+int do_init(Decoder *d, int bias, int start_state)
+{
+    if (bind(d)) return -1;
+    const uint32_t ss = start_state < 0 ? 0u : ((uint32_t)start_state & STATEMASK);
+    CU(launch_init(d->metrics[0], d->ctl, ss, bias, start_state < 0 ? -1 : 0, d->stream));
+    d->launches++;
+    if (sync_ctl(d)) return -1;
+    return 0;
+}
+
+TraceArgs trace_args(Decoder *d) { return TraceArgs{d->ring, d->row_fmt, d->len}; }
+
+// Run nbits trellis stages on device-resident symbols.  Returns renormalisation count or -1.
+int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1, int arg_s1 = -1)
+{
+    if (nbits <= 0) return 0;
+    // pos / renorm_count live in the control block; zero them for this call
+    CU(cudaMemsetAsync(&d->ctl->pos, 0, 2 * sizeof(int), d->stream));   // pos and renorm_count are adjacent
+    constexpr int BATCH_STAGES = 8192;
+    int pos = 0;
+    while (pos < nbits) {
+        const int end = std::min(nbits, pos + BATCH_STAGES);
+        if (d->time_kernels) CU(cudaEventRecord(d->kev0, d->stream));
+        unsigned long long n = 0;
+        int p = pos;
+        while (p < end) {
+            if (!d->force_single && !d->force_sat && end - p >= FK) {
+                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, p, d->force_careful};
+                CU(launch_fused(a, d->stream));
+                p += FK;
+            } else {
+                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, p, arg_s0 >= 0, arg_s0, arg_s1};
+                CU(launch_single(a, d->force_sat != 0, d->stream));
+                p += 1;
+            }
+            n++;
+        }
+        if (d->time_kernels) CU(cudaEventRecord(d->kev1, d->stream));
+        d->launches += n;
+        if (sync_ctl(d)) return -1;
+        if (d->time_kernels) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, d->kev0, d->kev1));
+            d->acs_ms += ms;
+            d->acs_launches_timed += n;
+        }
+        if (d->h_ctl->pos >= end) { pos = end; continue; }
+        // A pass declined to run: the reference's metrics are within 510*k of int16 saturation.
+        // Do that stage with the exact saturating kernel and carry on from there.
+        pos = d->h_ctl->pos;
+        SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, pos, arg_s0 >= 0, arg_s0, arg_s1};
+        CU(launch_single(a, true, d->stream));
+        d->launches++;
+        if (sync_ctl(d)) return -1;
+        if (d->h_ctl->pos != pos + 1) { set_err("saturating stage did not run (pos %d)", d->h_ctl->pos); return -1; }
+        pos += 1;
+    }
+    return d->h_ctl->renorm_count;
+}
+
+int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
+{
+    if (delay <= 0 || delay >= d->len) { set_err("stream decode needs 0 < delay < len (delay %d, len %d)", delay, d->len); return -1; }
+    const int chunk_max = d->len - delay;
+    int renorms = 0;
+    for (int done = 0; done < nbits;) {
+        const int n = std::min(chunk_max, nbits - done);
+        const long long T_first = d->h_ctl->T;
+        const int r = update_core(d, dev_syms + 2 * (size_t)done, n);
+        if (r < 0) return -1;
+        renorms += r;
+        CU(launch_stream_trace(trace_args(d), T_first, n, delay, dev_bits + done, d->stream));
+        d->launches++;
+        done += n;
+    }
+    CU(cudaStreamSynchronize(d->stream));
+    return renorms;
+}
+
+} // namespace
+
+// ==========================================================================================
+// the reference's nine entry points
+// ==========================================================================================
+extern "C" {
+
+void *create_viterbi224(int len)
+{
+    if (len <= 0) { set_err("create_viterbi224: len must be positive"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_err("create_viterbi224: no CUDA device (this library has no CPU path)");
+        return nullptr;
+    }
+    int dev = g_device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (cudaSetDevice(dev) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", dev); cudaGetLastError(); return nullptr; }
+
+    Decoder *d = static_cast<Decoder *>(calloc(1, sizeof(Decoder)));
+    if (!d) return nullptr;
+    d->magic = MAGIC;
+    d->dev = dev;
+    d->len = len;
+    d->chain_seg = 128;
+    d->chain_warm = 256;
+    d->ring_bytes = (size_t)len * ROWBYTES;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->metrics[0], METRICBYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->metrics[1], METRICBYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->row_fmt, (size_t)len) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->ctl, sizeof(Ctl)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->d_redo, sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->d_key, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->d_mnmx, 2 * sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->d_result, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->d_flag, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&d->h_ctl, sizeof(Ctl)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&d->h_result, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&d->kev0) == cudaSuccess && cudaEventCreate(&d->kev1) == cudaSuccess;
+    if (ok) {
+        d->ring = static_cast<uint32_t *>(pool_get(dev, d->ring_bytes));
+        ok = d->ring != nullptr;
+    }
+    // a fresh ring reads as zero (the reference's malloc'd ring is unspecified; zero is what a
+    // fresh mapping holds and what bitsync.c:245 style early reads rely on)
+    ok = ok && cudaMemsetAsync(d->ring, 0, d->ring_bytes, d->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(d->row_fmt, 0, (size_t)len, d->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(d->ctl, 0, sizeof(Ctl), d->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(d->d_redo, 0, sizeof(unsigned), d->stream) == cudaSuccess;
+    if (!ok) {
+        set_err("create_viterbi224(%d): device allocation failed: %s", len, cudaGetErrorString(cudaGetLastError()));
+        destroy(d);
+        return nullptr;
+    }
+    if (do_init(d, INIT_BIAS, 0)) { destroy(d); return nullptr; }     // viterbi224_sse2.c:78
+    return d;
+}
+
+int init_viterbi224(void *p, int starting_state)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    return do_init(d, INIT_BIAS, (int)((uint32_t)starting_state & STATEMASK));
+}
+
+int update_viterbi224_blk(void *p, const unsigned char *syms, int nbits)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits <= 0) return 0;
+    if (bind(d)) return -1;
+    if (nbits == 1)      // vdecode.c:145 -- the two symbols ride in the kernel arguments
+        return update_core(d, nullptr, 1, syms[0], syms[1]);
+    if (grow((void **)&d->dsyms, &d->dsyms_cap, 2 * (size_t)nbits)) return -1;
+    CU(cudaMemcpyAsync(d->dsyms, syms, 2 * (size_t)nbits, cudaMemcpyHostToDevice, d->stream));
+    return update_core(d, d->dsyms, nbits);
+}
+
+int chainback_viterbi224(void *p, unsigned char *data, unsigned int nbits, unsigned int endstate)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits == 0) return 0;
+    if (bind(d)) return -1;
+    const size_t nbytes = ((size_t)nbits + 7) / 8;
+    const int L = std::max(8, d->chain_seg & ~7);
+    const uint32_t nseg = (nbits + L - 1) / L;
+    if (grow((void **)&d->dout, &d->dout_cap, nbytes)) return -1;
+    if (grow((void **)&d->seg, &d->seg_cap, 2 * (size_t)nseg * sizeof(uint32_t))) return -1;
+    CU(launch_chainback(trace_args(d), nbits, endstate, L, d->chain_warm, d->dout, d->seg, d->seg + nseg, d->d_redo, d->stream));
+    d->launches += 2;
+    CU(cudaMemcpyAsync(data, d->dout, nbytes, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+static int walk(Decoder *d, int delay, int endstate)
+{
+    if (bind(d)) return -1;
+    const int use_argmin = endstate < 0;
+    if (use_argmin) {
+        CU(launch_argmin(d->metrics[d->h_ctl->cur], d->d_key, d->stream));
+        d->launches++;
+    }
+    const long long dp = d->h_ctl->T % d->len;
+    CU(launch_walk(trace_args(d), dp, delay, (uint32_t)endstate, use_argmin, d->d_key, d->d_result, d->stream));
+    d->launches++;
+    CU(cudaMemcpyAsync(d->h_result, d->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+int decodebit_viterbi224(void *p, int delay, int endstate)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (delay <= 0) return -1;
+    if (walk(d, delay, endstate)) return -1;
+    return (int)(long long)d->h_result[0];
+}
+
+unsigned long long decodeword_viterbi224(void *p, int delay, int endstate)
+{
+    Decoder *d = as_dec(p);
+    if (!d || delay <= 0) return 0;
+    if (walk(d, delay, endstate)) return 0;
+    return d->h_result[1];
+}
+
+static int metric_extreme(void *p, int want_max)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (bind(d)) return -1;
+    CU(launch_minmax(d->metrics[d->h_ctl->cur], d->d_mnmx, d->stream));
+    d->launches++;
+    unsigned mnmx[2];
+    CU(cudaMemcpyAsync(mnmx, d->d_mnmx, sizeof mnmx, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    const long long r = (long long)mnmx[want_max] - d->h_ctl->sub + d->h_ctl->O;    // reference-domain metric
+    return (int)(r + d->h_ctl->renormals);                                           // viterbi224_sse2.c:95,108
+}
+int max_metric_viterbi224(void *p) { return metric_extreme(p, 1); }
+int min_metric_viterbi224(void *p) { return metric_extreme(p, 0); }
+
+void delete_viterbi224(void *p)
+{
+    Decoder *d = as_dec(p);
+    if (d) destroy(d);
+}
+
+// ==========================================================================================
+// extensions
+// ==========================================================================================
+int v224x_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int v224x_set_device(int dev)
+{
+    int n = v224x_device_count();
+    if (dev < 0 || dev >= n) { set_err("v224x_set_device(%d): %d devices visible", dev, n); return -1; }
+    g_device = dev;
+    return 0;
+}
+const char *v224x_last_error(void) { return g_err; }
+const char *v224x_version(void) { return "viterbi224_b200 0.1 (sm_100a)"; }
+
+int v224x_init_uniform(void *p, int bias, int start_state)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (bias < 0 || bias > 20000) { set_err("bias out of range"); return -1; }
+    return do_init(d, bias, start_state < 0 ? -1 : (int)((uint32_t)start_state & STATEMASK));
+}
+
+int v224x_update_dev(void *p, const unsigned char *dev_syms, int nbits)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (bind(d)) return -1;
+    return update_core(d, dev_syms, nbits);
+}
+
+int v224x_stream_decode_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits <= 0) return 0;
+    if (bind(d)) return -1;
+    return stream_core(d, dev_syms, nbits, delay, dev_bits_out);
+}
+
+int v224x_stream_decode(void *p, const unsigned char *syms, int nbits, int delay, unsigned char *bits_out)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits <= 0) return 0;
+    if (bind(d)) return -1;
+    if (grow((void **)&d->dsyms, &d->dsyms_cap, 2 * (size_t)nbits)) return -1;
+    if (grow((void **)&d->dout, &d->dout_cap, (size_t)nbits)) return -1;
+    CU(cudaMemcpyAsync(d->dsyms, syms, 2 * (size_t)nbits, cudaMemcpyHostToDevice, d->stream));
+    const int r = stream_core(d, d->dsyms, nbits, delay, d->dout);
+    if (r < 0) return -1;
+    CU(cudaMemcpyAsync(bits_out, d->dout, (size_t)nbits, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return r;
+}
+
+void *v224x_dev_alloc(void *p, size_t bytes)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return nullptr;
+    void *q = nullptr;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) { set_err("cudaMalloc(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return q;
+}
+void v224x_dev_free(void *p, void *dev_ptr)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return;
+    cudaFree(dev_ptr);
+}
+int v224x_h2d(void *p, void *dev_dst, const void *host_src, size_t bytes)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    CU(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+int v224x_d2h(void *p, void *host_dst, const void *dev_src, size_t bytes)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+void *v224x_host_alloc_pinned(size_t bytes)
+{
+    void *q = nullptr;
+    if (cudaMallocHost(&q, bytes) != cudaSuccess) { set_err("cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return q;
+}
+void v224x_host_free_pinned(void *host_ptr) { if (host_ptr) cudaFreeHost(host_ptr); }
+
+int v224x_timer_start(void *p)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    CU(cudaStreamSynchronize(d->stream));
+    CU(cudaEventRecord(d->ev0, d->stream));
+    return 0;
+}
+float v224x_timer_stop_ms(void *p)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1.f;
+    if (cudaEventRecord(d->ev1, d->stream) != cudaSuccess || cudaEventSynchronize(d->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+int v224x_kernel_time_reset(void *p)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    d->acs_ms = 0; d->acs_launches_timed = 0;
+    return 0;
+}
+int v224x_kernel_time_enable(void *p, int on)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    d->time_kernels = on;
+    return 0;
+}
+float v224x_kernel_time_ms(void *p, unsigned long long *n_acs_launches)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1.f;
+    if (n_acs_launches) *n_acs_launches = d->acs_launches_timed;
+    return (float)d->acs_ms;
+}
+
+int v224x_get_stats(void *p, v224x_stats *out)
+{
+    Decoder *d = as_dec(p);
+    if (!d || !out) return -1;
+    if (bind(d)) return -1;
+    if (sync_ctl(d)) return -1;
+    unsigned redo = 0;
+    CU(cudaMemcpy(&redo, d->d_redo, sizeof redo, cudaMemcpyDeviceToHost));
+    out->launches = d->launches;
+    out->fused_passes = d->h_ctl->n_fused;
+    out->careful_passes = d->h_ctl->n_careful;
+    out->single_stages = d->h_ctl->n_single;
+    out->sat_stages = d->h_ctl->n_sat;
+    out->chainback_redo = redo;
+    out->renormals = d->h_ctl->renormals;
+    out->stages = d->h_ctl->T;
+    return 0;
+}
+
+int v224x_get_metrics(void *p, int16_t *host_out)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    int16_t *tmp = nullptr;
+    CU(cudaMalloc(&tmp, METRICBYTES));
+    int rc = 0;
+    do {
+        if (cudaMemsetAsync(d->d_flag, 0, sizeof(int), d->stream) != cudaSuccess) { rc = -1; break; }
+        if (launch_export_metrics(d->metrics[d->h_ctl->cur], d->ctl, tmp, d->d_flag, d->stream) != cudaSuccess) { rc = -1; break; }
+        d->launches++;
+        int flag = 0;
+        if (cudaMemcpyAsync(host_out, tmp, METRICBYTES, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess) { rc = -1; break; }
+        if (cudaMemcpyAsync(&flag, d->d_flag, sizeof(int), cudaMemcpyDeviceToHost, d->stream) != cudaSuccess) { rc = -1; break; }
+        if (cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = -1; break; }
+        if (flag) { set_err("metric outside the reference's int16 range"); rc = -1; }
+    } while (0);
+    cudaFree(tmp);
+    if (rc) cudaGetLastError();
+    return rc;
+}
+
+int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, long long stages)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    int16_t *tmp = nullptr;
+    CU(cudaMalloc(&tmp, METRICBYTES));
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(tmp, host_metrics, METRICBYTES, cudaMemcpyHostToDevice, d->stream) != cudaSuccess) { rc = -1; break; }
+        if (launch_import_metrics(d->metrics[d->h_ctl->cur], tmp, d->ctl, d->d_mnmx, renormals, stages, d->stream) != cudaSuccess) { rc = -1; break; }
+        d->launches += 3;
+        if (cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = -1; break; }
+    } while (0);
+    cudaFree(tmp);
+    if (rc) { set_err("v224x_set_state failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    return sync_ctl(d);
+}
+
+int v224x_get_row(void *p, int row, uint32_t *host_out)
+{
+    Decoder *d = as_dec(p);
+    if (!d || bind(d)) return -1;
+    if (row < 0 || row >= d->len) { set_err("row out of range"); return -1; }
+    uint32_t *tmp = nullptr;
+    CU(cudaMalloc(&tmp, ROWBYTES));
+    int rc = 0;
+    if (launch_export_row(trace_args(d), row, tmp, d->stream) != cudaSuccess) rc = -1;
+    d->launches++;
+    if (!rc && cudaMemcpyAsync(host_out, tmp, ROWBYTES, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess) rc = -1;
+    if (!rc && cudaStreamSynchronize(d->stream) != cudaSuccess) rc = -1;
+    cudaFree(tmp);
+    if (rc) { set_err("v224x_get_row failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    return 0;
+}
+
+int v224x_set_option(void *p, const char *key, long long value)
+{
+    Decoder *d = as_dec(p);
+    if (!d || !key) return -1;
+    if (!strcmp(key, "force_single")) d->force_single = (int)value;
+    else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
+    else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
+    else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
+    else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
+    else { set_err("unknown option %s", key); return -1; }
+    return 0;
+}
+
+} // extern "C"
