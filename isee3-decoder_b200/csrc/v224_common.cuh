@@ -21,6 +21,11 @@ constexpr size_t   METRICBYTES = (size_t)NSTATES * 2;   // 16 MiB
 
 constexpr int RENORM_TRIGGER = 25000;              // viterbi224_sse2.c:351
 constexpr int INIT_BIAS      = 5000;               // viterbi224_sse2.c:45 (SHRT_MIN+5000)
+// The packed 16-bit fast arithmetic compares metrics through a +0x8000 bias and needs
+// max - min + 510*8 to stay far below 2^15.  A legal trellis state never exceeds
+// 5000 + 23*510 = 16730 (any state is reachable from the best one in 23 stages); larger spreads
+// (only loadable through v224x_set_state) take the exact integer kernel instead.
+constexpr long long MAX_FAST_SPREAD = 24000;
 
 // Fused pass geometry: FK stages per HBM pass, done as two register rounds of FR stages.
 constexpr int FR = 4;
@@ -52,6 +57,7 @@ struct Ctl {
     int  cur;               // which metric buffer is the "old" one
     long long R0;           // reference metric of state 0 after the last stage (renorm trigger watch)
     long long maxR;         // largest reference metric after the last stage (saturation watch)
+    long long spread;       // max - min after the last stage (packed-arithmetic range watch)
     int  error;             // sticky: internal invariant violated
     unsigned ticket;        // CTA completion counter of the running pass
     // per-pass statistics, reset by the resolver

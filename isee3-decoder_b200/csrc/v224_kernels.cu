@@ -65,6 +65,7 @@ __device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
     c->O = O;
     c->R0 = (long long)z - mn + O;
     c->maxR = (long long)mx - mn + O;
+    c->spread = (long long)mx - mn;
     c->T += ks;
     c->pos += ks;
     c->cur ^= 1;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) k_init(uint16_t *m0, Ctl *c, uint32_t sta
         c->sub = 0;
         c->R0 = (start_state == 0 && start_value >= 0 ? start_value : bias) - 32768;
         c->maxR = bias - 32768;
+        c->spread = bias;
         c->cur = 0;
         c->error = 0;
         reset_stats(c);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
 
     // Every CTA takes the same go / no-go decision from the (quiescent) control block.
     if (c->pos != a.expected_pos || c->error) return;
-    if (c->maxR + 510ll * FK > 32767) return;                      // reference could saturate: host runs SAT stages
+    if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
     const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     const long long T0 = c->T;
     const uint32_t sub = (uint32_t)c->sub * 0x10001u;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
 {
     Ctl *c = a.ctl;
     if (c->pos != a.expected_pos || c->error) return;
-    if (!SAT && c->maxR + 510 > 32767) return;                     // reference could saturate: use the SAT variant
+    if (!SAT && (c->maxR + 510 > 32767 || c->spread > MAX_FAST_SPREAD)) return;   // reference could saturate: use the SAT variant
     const long long T0 = c->T;
     const int sub = c->sub;
     const long long O = c->O;
@@ -479,6 +481,7 @@ __global__ void k_import_ctl(Ctl *c, const uint16_t *m, const unsigned *mnmx, lo
     c->T = T;
     c->R0 = (long long)m[0] - 32768;
     c->maxR = (long long)mnmx[1] - 32768;
+    c->spread = (long long)mnmx[1] - (long long)mnmx[0];
     c->error = 0;
     reset_stats(c);
 }

@@ -1,0 +1,245 @@
+"""GPU tier (pytest -m gpu, on the B200 box): the CUDA path, called through the C ABI, against
+  * the golden fixtures recorded from the unmodified reference,
+  * the CPU checker (the reference itself if oracle/_ref travelled, else the oracle port) on fresh seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes (known-answer decode, idempotence,
+    block == per-bit streaming, checkpoint-window continuation).
+Bar: bit-exact (integer arithmetic): decoded bytes, every decision row, every path metric,
+renormalisation counts and min/max metrics."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import isee3_decoder_b200 as v224
+import pyoracle
+from scripts import run_script, compare_outcomes, crc
+
+pytestmark = pytest.mark.gpu
+S = v224.streams
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(f[:-4] for f in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if f.endswith(".npz"))
+
+
+def gpu_factory(**opts):
+    def make(n):
+        d = v224.Viterbi224(n)
+        for k, val in opts.items():
+            d.set_option(k, val)
+        return d
+    return make
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu(built):
+    # fail loudly rather than skip: -m gpu on a box without the CUDA path is a broken run
+    assert v224.device_count() > 0, "no CUDA device visible: the CUDA path cannot be exercised"
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (unmodified reference), every kernel variant
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_default_path(golden_cases, name):
+    case = golden_cases[name]
+    got = run_script(gpu_factory(), case["script"], case["syms"])
+    compare_outcomes(got, case["outcome"], f"gpu vs golden {name}")
+
+
+@pytest.mark.parametrize("opts", [{"force_single": 1}, {"force_sat": 1}, {"force_careful": 1}, {"chain_seg": 8, "chain_warm": 0},
+                                  {"chain_seg": 64, "chain_warm": 16}])
+@pytest.mark.parametrize("name", ["awgn1db_648_chunks", "erasure_304", "ringwrap_len40_200", "saturation_forced_72", "stream_d64_320"])
+def test_golden_kernel_variants(golden_cases, name, opts):
+    case = golden_cases[name]
+    got = run_script(gpu_factory(**opts), case["script"], case["syms"])
+    compare_outcomes(got, case["outcome"], f"gpu{opts} vs golden {name}")
+
+
+def test_golden_uses_the_fused_kernel(golden_cases):
+    case = golden_cases["awgn1db_648_chunks"]
+    with v224.Viterbi224(648) as d:
+        d.init(0)
+        d.update_blk(case["syms"], 648)
+        st = d.stats()
+    assert st["fused_passes"] == 81 and st["single_stages"] == 0 and st["sat_stages"] == 0, st
+    assert st["careful_passes"] >= 2, st           # two renormalisations happen in this stream
+
+
+def test_saturating_fallback_engages(golden_cases):
+    case = golden_cases["saturation_forced_72"]
+    got = run_script(gpu_factory(), case["script"], case["syms"])
+    compare_outcomes(got, case["outcome"], "saturation")
+    with v224.Viterbi224(80) as d:
+        m = np.random.default_rng(10).integers(27000, 32701, 1 << 23).astype(np.int16)
+        m[0] = 15000
+        m[1 << 22] = 15000
+        d.set_state(m, 0, 0)
+        d.update_blk(case["syms"], 72)
+        st = d.stats()
+    assert st["sat_stages"] >= 2, st               # stages where the reference's adds clip ran in the exact kernel
+    assert st["fused_passes"] >= 1, st             # and the decoder returned to the fused kernel afterwards
+
+
+# ---------------------------------------------------------------------------------------------
+# fresh inputs against the CPU checker
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ebn0,style,seed", [(1.0, "vtest", 31), (3.0, "symdemod", 32), (-1.0, "vtest", 33)])
+def test_frame_decode_equals_cpu_checker(ebn0, style, seed):
+    n = 328                                       # > one renormalisation period at 1 dB, not a multiple of 8*k
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, n, dtype=np.uint8)
+    bits[-24:] = 0
+    sym01, _ = S.encode_bits(bits, 0)
+    syms = S.awgn_vtest(sym01, ebn0, rng) if style == "vtest" else S.awgn_symdemod(sym01, ebn0, rng)
+    script = [["create", n], ["init", 0], ["update", 0, 200], ["minmax"], ["update", 200, 128], ["minmax"],
+              ["chainback", n, 0], ["decodebit", 100, -1], ["decodeword", 64, 0]]
+    Checker = pyoracle.best_cpu_decoder()
+    want = run_script(lambda k: Checker(k), script, syms)
+    got = run_script(gpu_factory(), script, syms)
+    compare_outcomes(got, want, f"gpu vs {Checker.kind}")
+
+
+def test_empty_and_degenerate_calls():
+    with v224.Viterbi224(16) as d:
+        assert d.update_blk(np.zeros(0, np.uint8), 0) == 0
+        assert d.chainback(0, 0).size == 0
+        assert d.decodebit(0, 0) == -1 and d.decodebit(-3, 0) == -1
+        assert d.init(0x7FFFFFFF) == 0                      # start state is masked to 23 bits (viterbi224_sse2.c:50)
+        m = d.get_metrics()
+        assert m[0x7FFFFF] == -32768 and m[0] == -32768 + 5000
+        assert d.min_metric() == -32768 and d.max_metric() == -32768 + 5000
+        # one single stage, one ragged block, ring wrap at len 16
+        syms = np.random.default_rng(1).integers(0, 256, 2 * 45, dtype=np.uint8)
+        with pyoracle.best_cpu_decoder()(16) as o:
+            o.init(0x7FFFFFFF)
+            for a, n in [(0, 1), (1, 17), (18, 27)]:
+                assert d.update_blk(syms[2 * a:], n) == o.update_blk(syms[2 * a:], n)
+            assert np.array_equal(d.get_metrics(), o.get_metrics())
+            for r in range(16):
+                assert crc(d.get_row(r)) == crc(o.get_row(r)), r
+            assert d.decodebit(15, 0) == o.decodebit(15, 0)
+            assert np.array_equal(d.chainback(45, 9), o.chainback(45, 9))
+
+
+def test_block_stream_equals_per_bit_abi_loop():
+    """v224x_stream_decode == the vdecode.c:145-152 loop through the nine-entry ABI (both on the GPU)."""
+    bits, syms = S.telemetry_stream(700, 3.0, seed=41)
+    delay = 96
+    with v224.Viterbi224(delay + 1) as d:                   # vdecode.c:94
+        d.init(0)
+        per_bit = np.empty(700, np.uint8)
+        ren = 0
+        for i in range(700):
+            ren += d.update_blk(syms[2 * i: 2 * i + 2], 1)
+            per_bit[i] = d.decodebit(delay, 0)
+        m1 = d.get_metrics()
+    with v224.Viterbi224(delay + 256) as d:                 # several chunks of 256
+        d.init(0)
+        blk, ren2 = d.stream_decode(syms, delay)
+        m2 = d.get_metrics()
+    assert ren == ren2
+    assert np.array_equal(m1, m2)
+    # the first `delay` outputs walk past the start of the stream; vdecode suppresses them (vdecode.c:151-158)
+    assert np.array_equal(per_bit[delay:], blk[delay:])
+    lag = delay + 22
+    assert np.array_equal(blk[lag:], bits[:700 - lag])       # and they are the transmitted data
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own programs on our library (drop-in), and the vdecode mirror
+# ---------------------------------------------------------------------------------------------
+def _bin(name):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not built (reference checkout absent at build time)")
+    return p
+
+
+def test_stock_vtest224_runs_on_the_gpu_library():
+    out = subprocess.run([_bin("vtest224_b200"), "-e", "3", "-l", "4096", "-n", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "BER 0/8192" in out.stdout and "FER 0/2" in out.stdout, out.stdout
+
+
+def test_stock_vdecode_on_gpu_library_and_block_mirror_agree_with_reference_output():
+    """One stream with an odd junk prefix (forces vdecode's phase flip, vdecode.c:126-133):
+    stock vdecode.c + reference decoder (fixture)  ==  stock vdecode.c + our library  ==  block-mode mirror."""
+    bits, soft = S.telemetry_stream(3 * 1024, 6.0, seed=11, junk_symbols=101)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "vdecode_flip_seed11.npy"))
+    mirror = v224.vdecode.vdecode(lambda n: v224.Viterbi224(n), soft, delay=64)
+    assert np.array_equal(mirror, fx)
+    out = subprocess.run([_bin("vdecode_b200"), "-d", "64", "-q"], input=soft.tobytes(), capture_output=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    assert np.array_equal(np.frombuffer(out.stdout, dtype=np.uint8), fx)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs)
+# ---------------------------------------------------------------------------------------------
+def test_config1_full_size_known_answer():
+    """vtest224 -l 10000 -e 3: create(10000) / init / update / chainback, BER 0 (vtest224.c:100-130)."""
+    data, syms = S.vtest_frame(10000, 3.0, seed=1001)
+    with v224.Viterbi224(10000) as d:
+        d.init(0)
+        d.update_blk(syms, 10000)
+        out = d.chainback(10000, 0)
+        assert np.array_equal(out, data)
+        out2 = d.chainback(10000, 0)                 # traceback is idempotent
+        assert np.array_equal(out, out2)
+        d.set_option("chain_seg", 10000)             # one serial segment == speculative segments
+        assert np.array_equal(d.chainback(10000, 0), out)
+        assert d.stats()["fused_passes"] == 1250
+
+
+def test_long_delay_stream_and_checkpoint_window():
+    """Config 3/4 in miniature: long stream at 2 dB, delay 2048, then the SURVEY 8c window check --
+    dump the GPU state mid-stream, continue 40 stages on the CPU checker and on the GPU, compare everything."""
+    n = 40000
+    rng = np.random.default_rng(77)
+    bits = rng.integers(0, 2, n, dtype=np.uint8)
+    sym01, _ = S.encode_bits(bits, 0)
+    syms = S.awgn_vtest(sym01, 2.0, rng)
+    delay = 2048
+    with v224.Viterbi224(delay + 4096) as d:
+        d.init(0)
+        out, ren = d.stream_decode(syms, delay)
+        lag = delay + 22
+        errs = int((out[lag:] != bits[:n - lag]).sum())
+        assert errs == 0, errs                       # 2 dB is far above this code's threshold
+        assert ren >= n // 400                       # renormalisations happened (about one per 280 bits at these levels)
+        st = d.stats()
+        assert st["sat_stages"] == 0
+        m = d.get_metrics()
+        renormals = st["renormals"]
+        # continue on both sides from the dumped state
+        tail_bits = rng.integers(0, 2, 40, dtype=np.uint8)
+        tsym01, _ = S.encode_bits(tail_bits, int("".join(map(str, bits[-24:])), 2))
+        tsyms = S.awgn_vtest(tsym01, 2.0, rng)
+        with pyoracle.best_cpu_decoder()(delay + 4096) as o:
+            o.set_state(m, renormals, n)
+            r_cpu = o.update_blk(tsyms, 40)
+            r_gpu = d.update_blk(tsyms, 40)
+            assert r_cpu == r_gpu
+            assert np.array_equal(o.get_metrics(), d.get_metrics())
+            assert o.min_metric() == d.min_metric() and o.max_metric() == d.max_metric()
+            for k in range(40):
+                row = (n + k) % (delay + 4096)
+                assert crc(o.get_row(row)) == crc(d.get_row(row)), k
+
+
+def test_time_segmented_decode_matches_single_pass():
+    """Multi-GPU partitioning run on one GPU: segments with warm-up reproduce the single-pass output
+    wherever survivors merged inside the warm-up; residual differences are counted (north_star)."""
+    n = 24000
+    bits, syms = S.telemetry_stream(n, 3.0, seed=55)
+    delay = 200
+    with v224.Viterbi224(delay + 4096) as d:
+        d.init(0)
+        full, _ = d.stream_decode(syms, delay)
+        parts = []
+        for seg in v224.segments.plan(n, 4, warmup=1024, delay=delay):
+            parts.append(v224.segments.decode_segment(d, syms, seg, delay))
+    seg_out = v224.segments.stitch(parts)
+    assert seg_out.size == n
+    diff = int((seg_out != full).sum())
+    assert diff == 0, f"{diff} residual differences vs single pass"
