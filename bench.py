@@ -341,7 +341,7 @@ def main():
                              "frac_unfused_equivalent": value / world * B_STAGE_UNFUSED / 1e9 / peak},
                 "clocks": clocks,
                 "check": {"bit_errors_vs_transmitted": int(errs_total), "bits_checked": int(nchk_total), "phase_flips_rank0": wl["flips"],
-                          "wall_ms_per_step": wall_max * 1e3 / args.steps,
+                          "wall_ms_per_step": wall_max / args.steps,
                           "passes": {k: st[k] for k in ("fused_passes", "careful_passes", "single_stages", "sat_stages")}}}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()

@@ -66,7 +66,14 @@ static inline uint32_t f_maxu2(uint32_t a, uint32_t b)
 namespace v224 {
 V224_HD uint32_t f_popc(uint32_t x) { return (uint32_t)__popc(x); }
 V224_HD uint32_t f_addmin_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }   // VIADDMNMX.U16x2
-V224_HD uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }             // PRMT
+// PRMT in its default mode: bit 3 of a selector nibble replicates the selected byte's sign bit.
+// (__byte_perm() masks the selector to 3 bits per nibble and would drop that.)
+V224_HD uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 V224_HD uint32_t f_minu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }                                   // VIMNMX.U16x2
 V224_HD uint32_t f_maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 }

@@ -55,3 +55,26 @@ def decode_segment(decoder, soft, seg, delay):
 
 def stitch(parts):
     return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def decode_distributed(decoder, soft, nbits, delay, warmup, rank, world_size, dist=None):
+    """One rank's part of a time-segmented decode plus the gather of all ranks' output bits.
+    `dist` is torch.distributed (already initialised; nccl or gloo) or None for world_size 1.
+    Returns the full uint8[nbits] output on every rank.  The only communication is the final
+    all_gather of decoded bits (1 byte per bit here; nothing crosses ranks inside the hot loop)."""
+    segs = plan(nbits, world_size, warmup, delay)
+    mine = decode_segment(decoder, soft, segs[rank], delay)
+    if dist is None or world_size == 1:
+        return mine
+    import torch
+    longest = max(s.out_last - s.out_first for s in segs)
+    buf = torch.zeros(longest, dtype=torch.uint8)
+    buf[: mine.size] = torch.from_numpy(mine)
+    dev = None
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = buf.to(dev)
+    outs = [torch.zeros_like(buf) for _ in range(world_size)]
+    dist.all_gather(outs, buf)
+    parts = [o.cpu().numpy()[: s.out_last - s.out_first] for o, s in zip(outs, segs)]
+    return stitch(parts)

@@ -1,0 +1,114 @@
+"""CPU tier: host-side logic that sits around the CUDA path -- the vdecode.c symbol pairing / phase
+flip mirror, the time-segment planner, and the two-rank (gloo) gather."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import isee3_decoder_b200 as v224
+
+S = v224.streams
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def vdecode_pairs_literal(soft, start_phase=0, dontflip=False):
+    """vdecode.c:101-187 transcribed symbol by symbol (test-side restatement; slow on purpose)."""
+    sync_vector = S.sync_vector().tolist()
+    old = [0] * 4096
+    for i in range(0, 4096, 2):
+        old[i] = 255 if S.G1FLIP else 0
+        old[i + 1] = 255 if S.G2FLIP else 0
+    symbols = start_phase
+    vdsyms = [0, 0]
+    sync_count = 0
+    peak_in = peak_out = -1000000
+    pairs = []
+    for c in soft.tolist():
+        old[symbols] = c
+        vdsyms[symbols % 2] = c
+        if not dontflip:
+            ssum = 0
+            for k in range(34):
+                v = old[(4096 + symbols + k - 33) % 4096] - 128
+                ssum += v if sync_vector[k] else -v
+            if symbols % 2 == 0:
+                peak_out = max(peak_out, ssum)
+            else:
+                peak_in = max(peak_in, ssum)
+                sync_count += 1
+                if sync_count >= 2048:
+                    sync_count = 0
+                    if peak_out > peak_in:
+                        symbols = symbols + 1 if symbols % 2 == 0 else symbols - 1
+                    peak_in = peak_out = -1000000
+        if symbols % 2 == 1:
+            pairs.append((vdsyms[0], vdsyms[1]))
+        symbols = (symbols + 1) % 4096
+    return np.array(pairs, dtype=np.uint8).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("junk,start_phase,dontflip", [(0, 0, False), (101, 0, False), (7, 1, False), (101, 0, True), (4097, 0, False)])
+def test_pair_symbols_equals_literal_vdecode_loop(junk, start_phase, dontflip):
+    _, soft = S.telemetry_stream(5 * 1024, 5.0, seed=100 + junk, junk_symbols=junk)
+    a = v224.vdecode.pair_symbols(soft, start_phase, dontflip)
+    b = vdecode_pairs_literal(soft, start_phase, dontflip)
+    assert a.shape == b.shape
+    assert np.array_equal(a, b)
+
+
+def test_phase_flip_happens_once_for_odd_junk():
+    _, soft = S.telemetry_stream(6 * 1024, 5.0, seed=5, junk_symbols=33)
+    pairs, flips = v224.vdecode.pair_symbols(soft, return_flips=True)
+    assert flips == [4095]
+    assert pairs.shape[0] == (soft.size - 1) // 2       # one symbol is dropped by the flip
+    _, soft = S.telemetry_stream(6 * 1024, 5.0, seed=5, junk_symbols=32)
+    _, flips = v224.vdecode.pair_symbols(soft, return_flips=True)
+    assert flips == []
+
+
+def test_segment_plan_covers_stream_exactly_once():
+    for nbits, world, warm, delay in [(1000, 1, 64, 24), (1000, 3, 64, 200), (1 << 20, 8, 2048, 200), (17, 4, 8, 4)]:
+        segs = v224.segments.plan(nbits, world, warm, delay)
+        assert segs[0].out_first == 0 and segs[-1].out_last == nbits
+        for a, b in zip(segs, segs[1:]):
+            assert a.out_last == b.out_first
+        for s in segs:
+            assert s.stage_first == max(0, s.out_first - max(warm, delay))
+            assert s.skip == s.out_first - s.stage_first
+            assert s.nstages == s.out_last - s.stage_first
+
+
+def test_reencode_tally_is_zero_on_clean_stream():
+    bits, soft = S.telemetry_stream(2048, 30.0, seed=9)          # effectively noiseless
+    pairs = v224.vdecode.pair_symbols(soft, dontflip=True)
+    delay = 64
+    lag = delay + 22
+    out = np.concatenate([np.zeros(lag, np.uint8), bits])[: pairs.shape[0]]   # what the decoder would emit
+    # bit i of `out` after the startup is data bit i - lag; re-encoding it must reproduce the received hard symbols
+    errs = v224.vdecode.reencode_symbol_errors(out[delay:], pairs, delay)   # vdecode prints from pair `delay` on
+    assert errs == 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_segmented_decode_gloo(built):
+    """world_size 2 over gloo on CPU: partition, warm-up, gather.  The CPU oracle stands in for the GPU
+    decoder so that the host logic of the N>1 path is covered without a GPU."""
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_segment_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "RESULT diff=0 data_ok=True n=144" in outs[0], outs[0]
