@@ -61,6 +61,7 @@ float v224x_timer_stop_ms(void *p);              /* record + synchronise, elapse
 int   v224x_kernel_time_reset(void *p);
 int   v224x_kernel_time_enable(void *p, int on);
 float v224x_kernel_time_ms(void *p, unsigned long long *n_acs_launches);
+unsigned long long v224x_kernel_time_passes(void *p);   /* 8-stage passes inside the timed launches */
 
 /* ---- counters --------------------------------------------------------------------------- */
 typedef struct {
@@ -69,6 +70,7 @@ typedef struct {
     unsigned long long careful_passes; /* ... of which recorded per-stage minima                */
     unsigned long long single_stages;  /* 1-stage passes (fast arithmetic)                      */
     unsigned long long sat_stages;     /* 1-stage passes (exact saturating arithmetic)          */
+    unsigned long long invalidated_passes; /* fused passes discarded by the saturation validation  */
     unsigned long long chainback_redo; /* speculative chainback segments that had to be redone  */
     long long          renormals;      /* the reference's `renormals` accumulator               */
     long long          stages;         /* trellis stages since the last init                    */
@@ -84,7 +86,8 @@ int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, l
  * decision of new state s (viterbi224_sse2.c:141). */
 int v224x_get_row(void *p, int row, uint32_t *host_out);
 /* Knobs: "force_single"=1 never fuse, "force_sat"=1 exact saturating single stages only,
- * "force_careful"=1 always record per-stage minima, "chain_seg"/"chain_warm" chainback
+ * "force_careful"=1 always record per-stage minima, "per_pass_launch"=1 one kernel launch per
+ * 8-stage pass instead of the persistent multi-pass kernel, "chain_seg"/"chain_warm" chainback
  * segment length / warm-up depth. */
 int v224x_set_option(void *p, const char *key, long long value);
 

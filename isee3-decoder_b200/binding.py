@@ -16,7 +16,7 @@ ABI_SYMBOLS = ["create_viterbi224", "init_viterbi224", "update_viterbi224_blk", 
 EXT_SYMBOLS = ["v224x_device_count", "v224x_set_device", "v224x_last_error", "v224x_version", "v224x_stream_decode",
                "v224x_stream_decode_dev", "v224x_update_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
                "v224x_h2d", "v224x_d2h", "v224x_host_alloc_pinned", "v224x_host_free_pinned", "v224x_timer_start",
-               "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms",
+               "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms", "v224x_kernel_time_passes",
                "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option"]
 
 
@@ -26,7 +26,8 @@ class V224Error(RuntimeError):
 
 class Stats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_ulonglong), ("fused_passes", ctypes.c_ulonglong), ("careful_passes", ctypes.c_ulonglong),
-                ("single_stages", ctypes.c_ulonglong), ("sat_stages", ctypes.c_ulonglong), ("chainback_redo", ctypes.c_ulonglong),
+                ("single_stages", ctypes.c_ulonglong), ("sat_stages", ctypes.c_ulonglong), ("invalidated_passes", ctypes.c_ulonglong),
+                ("chainback_redo", ctypes.c_ulonglong),
                 ("renormals", ctypes.c_longlong), ("stages", ctypes.c_longlong)]
 
 
@@ -76,6 +77,7 @@ def load_library():
         "v224x_kernel_time_reset": (ci, [vp]),
         "v224x_kernel_time_enable": (ci, [vp, ci]),
         "v224x_kernel_time_ms": (ctypes.c_float, [vp, ctypes.POINTER(ctypes.c_ulonglong)]),
+        "v224x_kernel_time_passes": (ctypes.c_ulonglong, [vp]),
         "v224x_get_stats": (ci, [vp, ctypes.POINTER(Stats)]),
         "v224x_get_metrics": (ci, [vp, vp]),
         "v224x_set_state": (ci, [vp, vp, cll, cll]),
@@ -214,7 +216,7 @@ class Viterbi224:
     def kernel_time_ms(self):
         n = ctypes.c_ulonglong(0)
         ms = float(self.lib.v224x_kernel_time_ms(self.h, ctypes.byref(n)))
-        return ms, int(n.value)
+        return ms, int(n.value), int(self.lib.v224x_kernel_time_passes(self.h))
 
     def stats(self):
         s = Stats()

@@ -34,6 +34,12 @@ constexpr int FUSED_TILE_COLS = 64;                // columns (j) per tile
 constexpr int FUSED_THREADS   = 128;               // 16 row-groups x 8 column groups
 constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512
 
+// Path-metric buffers rotate A -> B -> C -> A.  Three (not two) so that, in the persistent kernel,
+// pass n+1 may already be writing while pass n is still being validated: pass n's input stays
+// intact until pass n is resolved, which makes an invalidated pass restartable.
+constexpr int NBUF = 3;
+constexpr int PSLOTS = 4;                          // in-flight pass bookkeeping slots (ring)
+
 // Decision-row formats (row_fmt[] tags).  0 = canonical (bit index = new-state number, the
 // reference's layout, viterbi224_sse2.c:141,324); t in 1..FK = written by stage t of a fused
 // pass in that kernel's thread-major layout (see fused_bit_address()).
@@ -47,6 +53,28 @@ constexpr uint8_t ROWFMT_CANON = 0;
 // R = P + O for the 64-bit offset O below.  Decisions depend on metric differences only, so
 // any O is exact as long as neither side saturates; the resolver tracks the reference's
 // renormalisation test (viterbi224_sse2.c:351-377) on R virtually and keeps P small.
+// Bookkeeping of one in-flight pass of the persistent kernel.
+struct PassSlot {
+    unsigned s0[FK + 1];    // P of state 0 after stage t
+    unsigned minP[FK + 1];  // global min of P after stage t ([FK] always, the others in careful passes)
+    unsigned maxP;          // global max of P after the last stage
+    unsigned done[2];       // finished tiles by parity of the tile index (what the next pass waits on)
+    unsigned done_total;
+    int sub;                // what this pass subtracts from every P while loading
+    int careful;            // this pass records per-stage minima
+};
+struct PersistCtl {
+    unsigned next_item;     // work queue head: item = pass * 512 + order index
+    unsigned resolved_upto; // number of passes resolved (in order)
+    int stop_pass;          // passes >= stop_pass must not run (saturation watch / invalidated pass)
+    int npasses;
+    int force_careful;
+    int pad;
+    long long Ostore;       // R = P_stored + Ostore for the output of the last resolved pass
+    long long maxR_prev;    // largest reference metric at the output of the last resolved pass
+    PassSlot slot[PSLOTS];
+};
+
 struct Ctl {
     long long O;            // R = P + O
     long long renormals;    // the reference's running `renormals` (viterbi224_sse2.c:33,367)
@@ -65,7 +93,8 @@ struct Ctl {
     unsigned minP[FK + 1];  // global min of P after stage t (careful passes; [k] always)
     unsigned maxP_end;      // global max of P after the last stage
     // counters for tests / bench
-    unsigned n_fused, n_single, n_careful, n_sat;
+    unsigned n_fused, n_single, n_careful, n_sat, n_invalidated;
+    PersistCtl pc;
 };
 
 // where a fused-format decision bit lives: stage t (1..FK), state s after that stage.

@@ -68,7 +68,7 @@ __device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
     c->spread = (long long)mx - mn;
     c->T += ks;
     c->pos += ks;
-    c->cur ^= 1;
+    c->cur = (c->cur + 1) % NBUF;
     reset_stats(c);
 }
 
@@ -109,44 +109,35 @@ struct __align__(16) FusedSmem {
 };
 
 template <int T>
-__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, const FusedArgs &a,
-                                            Ctl *c, long long T0, bool careful, uint32_t chunk)
+__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t *ring, uint8_t *row_fmt,
+                                            int len, unsigned *s0, unsigned *minP, long long T0, bool careful, bool first, uint32_t chunk)
 {
     uint32_t dw[4];
     acs_stage<T>(A, pbase, optab, dw);
-    const long long row = (T0 + T - 1) % a.len;
-    st_cs_v4(reinterpret_cast<uint8_t *>(a.ring) + (size_t)row * ROWBYTES + (size_t)chunk * 16, make_uint4(dw[0], dw[1], dw[2], dw[3]));
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        c->s0[T] = A[0][0] & 0xffffu;            // slot 0 always holds state 0
-        a.row_fmt[row] = (uint8_t)T;
+    const long long row = (T0 + T - 1) % len;
+    st_cs_v4(reinterpret_cast<uint8_t *>(ring) + (size_t)row * ROWBYTES + (size_t)chunk * 16, make_uint4(dw[0], dw[1], dw[2], dw[3]));
+    if (first) {
+        s0[T] = A[0][0] & 0xffffu;               // slot 0 always holds state 0
+        row_fmt[row] = (uint8_t)T;
     }
     if (careful && T < FK) {
         uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
-        if ((threadIdx.x & 31) == 0) atomicMin(&c->minP[T], mn);
+        if ((threadIdx.x & 31) == 0) atomicMin(&minP[T], mn);
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
+// The body shared by the per-pass kernel and the persistent kernel: one tile, eight stages.
+// LDCG: metrics are read through L2 only (another SM wrote them, possibly within this launch).
+__device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, uint16_t *newm, uint32_t *ring, uint8_t *row_fmt, int len,
+                                           const uint8_t *sym, unsigned *s0, unsigned *minP, unsigned *maxP, long long T0, uint32_t sub,
+                                           bool careful, uint32_t tau)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
-    Ctl *c = a.ctl;
-
-    // Every CTA takes the same go / no-go decision from the (quiescent) control block.
-    if (c->pos != a.expected_pos || c->error) return;
-    if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
-    const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
-    const long long T0 = c->T;
-    const uint32_t sub = (uint32_t)c->sub * 0x10001u;
-    const uint16_t *oldm = a.metrics[c->cur];
-    uint16_t *newm = a.metrics[c->cur ^ 1];
-
-    const uint32_t tid = threadIdx.x, tau = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
     const uint32_t thr = tid >> 3, g = tid & 7;                    // row group, column group
     const uint32_t chunk = tau * FUSED_THREADS + tid;
+    const bool first = tau == 0 && tid == 0;
 
     // operand table for the 8 symbol pairs of this pass
-    const uint8_t *sym = a.syms + 2 * (size_t)a.expected_pos;
     for (int e = tid; e < OPTAB_WORDS; e += FUSED_THREADS) sm.optab[e] = optab_entry(e, sym);
 
     // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 8 columns ----
@@ -155,17 +146,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
         const uint4 *src = reinterpret_cast<const uint4 *>(oldm) + ((size_t)thr * 32768 + tau * FUSED_TILE_COLS + g * 8) / 8;
 #pragma unroll
         for (int mh = 0; mh < 16; mh++) {
-            const uint4 v = src[(size_t)mh * 16 * 32768 / 8];
+            const uint4 v = __ldcg(src + (size_t)mh * 16 * 32768 / 8);
             A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][2] = v.z - sub; A[mh][3] = v.w - sub;
         }
     }
     __syncthreads();                                               // optab ready
     {
         const uint32_t pbase = (thr << 15) | (tau << 6) | (g << 3);
-        fused_stage<1>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<2>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<3>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<4>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
     }
     // ---- exchange: rows m = mh*16 + ml, 128 B per row ----
     {
@@ -182,16 +173,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
     // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
     {
         const uint32_t pbase = (thr << 19) | (tau << 6) | (g << 3);
-        fused_stage<5>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<6>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<7>(A, pbase, sm.optab, a, c, T0, careful, chunk);
-        fused_stage<8>(A, pbase, sm.optab, a, c, T0, careful, chunk);
+        fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
+        fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
     }
     // ---- statistics of the final stage ----
     {
         const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
         const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
-        if ((tid & 31) == 0) { atomicMin(&c->minP[FK], mn); atomicMax(&c->maxP_end, mx); }
+        if ((tid & 31) == 0) { atomicMin(&minP[FK], mn); atomicMax(maxP, mx); }
     }
     // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B ----
     {
@@ -207,17 +198,200 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    Ctl *c = a.ctl;
+
+    // Every CTA takes the same go / no-go decision from the (quiescent) control block.
+    if (c->pos != a.expected_pos || c->error) return;
+    if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
+    const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
+    fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.syms + 2 * (size_t)a.expected_pos,
+               c->s0, c->minP, &c->maxP_end, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x);
+
     // ---- last CTA resolves the pass ----
     __shared__ unsigned s_ticket;
-    __threadfence();
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&c->ticket, 1u);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(&c->ticket, 1u);
+    }
     __syncthreads();
-    if (s_ticket == gridDim.x - 1 && tid == 0) {
+    if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) {
         __threadfence();
         if (careful) c->n_careful++;
         c->n_fused++;
         resolve_pass(c, FK, careful, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent multi-pass kernel: one launch runs `npasses` 8-stage passes as a dataflow
+// ------------------------------------------------------------------------------------------
+// Work item = (pass n, tile tau), taken from an atomic queue in pass-major order.  Tile tau of pass
+// n+1 reads, for every row m, 64 states out of pass n's output tile 2m + (tau >> 8): it depends on
+// exactly the even (tau < 256) or the odd (tau >= 256) tiles of pass n.  Each pass therefore runs
+// its even tiles first; the next pass starts as soon as those are out, while the odd tiles are still
+// in flight -- no grid-wide barrier, no launch gap.  The statistics of pass n are only complete when
+// the pass is, so pass n+2 is the first that can use them: `sub` and the careful flag lag two passes.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void slot_reset(PassSlot &s)
+{
+#pragma unroll
+    for (int t = 0; t <= FK; t++) { s.s0[t] = 0; s.minP[t] = 0xffffffffu; }
+    s.maxP = 0;
+    s.done[0] = s.done[1] = 0;
+    s.done_total = 0;
+}
+
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful)
+{
+    PersistCtl &pc = c->pc;
+    pc.next_item = 0;
+    pc.resolved_upto = 0;
+    pc.npasses = npasses;
+    pc.force_careful = force_careful;
+    pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
+    pc.maxR_prev = c->maxR;
+    for (int i = 0; i < PSLOTS; i++) slot_reset(pc.slot[i]);
+    pc.slot[0].sub = c->sub;
+    pc.slot[1].sub = 0;
+    pc.slot[0].careful = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
+    pc.slot[1].careful = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
+    int stop = npasses;
+    if (c->spread > MAX_FAST_SPREAD || c->error) stop = 0;
+    // non-careful passes are not validated stage by stage: keep them well away from saturation
+    if (!pc.slot[0].careful && c->maxR + 510ll * FK > 32767) stop = 0;
+    if (stop > 1 && !pc.slot[1].careful && c->maxR + 510ll * 2 * FK > 32767) stop = 1;
+    pc.stop_pass = stop;
+}
+
+// Resolve pass n (run by the thread that completed the pass's last tile).  Replays the reference's
+// renormalisation test per stage, validates that the reference could not have saturated, commits
+// the pass (or invalidates it), and publishes the parameters of pass n+2.
+__device__ void resolve_persist(Ctl *c, int n)
+{
+    PersistCtl &pc = c->pc;
+    while ((int)ld_acquire(&pc.resolved_upto) != n) __nanosleep(64);
+    PassSlot &sl = pc.slot[n % PSLOTS];
+    const bool careful = sl.careful != 0;
+    bool valid = !c->error && n < *(volatile int *)&pc.stop_pass;
+    long long O = pc.Ostore + sl.sub;                  // offset of the values this pass loaded
+    long long maxR = pc.maxR_prev;                     // exact at pass start; +510 per stage bounds it inside
+    long long renormals = 0;
+    int count = 0;
+    for (int t = 1; valid && t <= FK; t++) {
+        // the adds of stage t clip in the reference iff some R + branch metric exceeds SHRT_MAX (:296-299)
+        if (maxR + 510 > 32767) { valid = false; break; }
+        maxR += 510;
+        const long long R0 = (long long)sl.s0[t] + O;
+        if (R0 >= RENORM_TRIGGER) {                                        // viterbi224_sse2.c:351
+            if (!(careful || t == FK) || sl.minP[t] == 0xffffffffu) { c->error |= 1; valid = false; break; }
+            const long long minR = (long long)sl.minP[t] + O;             // :358-366
+            renormals += (minR < 0 ? minR + 65536 : minR) + 32768;        // :354,:366,:367 (uint16 read of the minimum)
+            count++;
+            O -= minR + 32768;                                             // :373
+            maxR -= minR + 32768;
+        }
+    }
+    const unsigned mn = sl.minP[FK], mx = sl.maxP, z = sl.s0[FK];
+    if (valid && (mn == 0xffffffffu || mx < mn)) { c->error |= 2; valid = false; }
+    if (valid && (long long)mx - mn > MAX_FAST_SPREAD) valid = false;
+    if (valid) {
+        pc.Ostore = O;
+        pc.maxR_prev = (long long)mx + O;
+        c->renormals += renormals;
+        c->renorm_count += count;
+        // external view (what the host and the single-stage kernel see between launches)
+        c->sub = (int)mn;
+        c->O = O + mn;
+        c->R0 = (long long)z + O;
+        c->maxR = (long long)mx + O;
+        c->spread = (long long)mx - mn;
+        c->T += FK;
+        c->pos += FK;
+        c->cur = (c->cur + 1) % NBUF;
+        c->n_fused++;
+        if (careful) c->n_careful++;
+        // parameters of pass n+2 (its slot is free: pass n-2 is long resolved)
+        PassSlot &nx = pc.slot[(n + 2) % PSLOTS];
+        slot_reset(nx);
+        nx.sub = (int)mn - pc.slot[(n + 1) % PSLOTS].sub;                  // <= min of pass n+1's output, >= 0
+        nx.careful = pc.force_careful || ((long long)z + O + 510ll * 2 * FK >= RENORM_TRIGGER);
+        if (!nx.careful && (long long)mx + O + 510ll * 2 * FK > 32767) {
+            if (n + 2 < pc.stop_pass) pc.stop_pass = n + 2;
+        }
+    } else {
+        // the pass (and anything that already consumed its output) is discarded; its input buffer is intact
+        if (n < pc.stop_pass) { pc.stop_pass = n; c->n_invalidated++; }
+    }
+    __threadfence();
+    st_release(&pc.resolved_upto, (unsigned)(n + 1));
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_persist(PersistArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    Ctl *c = a.ctl;
+    PersistCtl &pc = c->pc;
+    __shared__ unsigned s_item;
+    __shared__ int s_go, s_sub, s_careful, s_cur;
+    __shared__ long long s_T;
+    const uint32_t tid = threadIdx.x;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(&pc.next_item, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        const int n = (int)(item >> 9);
+        if (n >= a.npasses) break;
+        // even tiles of a pass first (the next pass's first half waits only for them)
+        const unsigned w = item & 511u, cls = w >> 7, idx = w & 127u;
+        const uint32_t tau = ((cls & 1u) << 8) | (idx << 1) | (cls >> 1);
+        PassSlot &sl = pc.slot[n % PSLOTS];
+        if (tid == 0) {
+            while ((int)ld_acquire(&pc.resolved_upto) < n - 1) __nanosleep(100);      // parameters of pass n exist
+            int go = n < *(volatile int *)&pc.stop_pass;
+            if (go && n > 0) {
+                const unsigned *dep = &pc.slot[(n - 1) % PSLOTS].done[tau >> 8];
+                while (ld_acquire(dep) < 256u) {
+                    __nanosleep(40);
+                    if (n >= *(volatile int *)&pc.stop_pass) { go = 0; break; }
+                }
+            }
+            s_go = go;
+            s_sub = *(volatile int *)&sl.sub;
+            s_careful = *(volatile int *)&sl.careful;
+            // the first pass of the launch starts from the control block's buffer / stage counter;
+            // both advance by one per resolved pass, so pass n is at a fixed offset from the launch state
+            s_cur = a.cur0;
+            s_T = a.T0;
+        }
+        __syncthreads();
+        if (!s_go) break;
+        const int cur = (s_cur + n) % NBUF;
+        fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.syms + 2 * ((size_t)a.pos0 + (size_t)n * FK),
+                   sl.s0, sl.minP, &sl.maxP, s_T + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, tau);
+        __syncthreads();                       // every thread's stores and statistics are issued
+        if (tid == 0) {
+            __threadfence();                   // ... and visible GPU-wide before the tile counts as done
+            atomicAdd(&sl.done[tau & 1u], 1u);
+            if (atomicAdd(&sl.done_total, 1u) == FUSED_TILES - 1) resolve_persist(c, n);
+        }
     }
 }
 
@@ -235,7 +409,7 @@ __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
     const int sub = c->sub;
     const long long O = c->O;
     const uint16_t *oldm = a.metrics[c->cur];
-    uint16_t *newm = a.metrics[c->cur ^ 1];
+    uint16_t *newm = a.metrics[(c->cur + 1) % NBUF];
     const int s0 = a.use_arg_syms ? a.sym0 : a.syms[2 * (size_t)a.expected_pos];
     const int s1 = a.use_arg_syms ? a.sym1 : a.syms[2 * (size_t)a.expected_pos + 1];
 
@@ -505,6 +679,29 @@ cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st)
         g_fused_attr_set[dev] = true;
     }
     k_acs_fused<<<FUSED_TILES, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_persist(const PersistArgs &a, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64];
+    static int grid_cap[64];
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, FUSED_THREADS, sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        grid_cap[dev] = per_sm * sms;
+        attr_set[dev] = true;
+    }
+    k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful);
+    const long long items = (long long)a.npasses * FUSED_TILES;
+    const int grid = (int)(items < grid_cap[dev] ? items : grid_cap[dev]);
+    k_acs_persist<<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)

@@ -6,7 +6,7 @@ namespace v224 {
 
 struct FusedArgs {
     Ctl *ctl;
-    uint16_t *metrics[2];
+    uint16_t *metrics[NBUF];
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;     // device symbols of the running update call (2 per bit)
@@ -15,9 +15,23 @@ struct FusedArgs {
     int force_careful;       // test knob: record per-stage minima regardless
 };
 
+struct PersistArgs {
+    Ctl *ctl;
+    uint16_t *metrics[NBUF];
+    uint32_t *ring;
+    uint8_t *row_fmt;
+    const uint8_t *syms;     // symbols of the running update call; this launch starts at stage pos0
+    int len;
+    int pos0;                // stages of this call already done when the launch starts
+    int cur0;                // metric buffer holding the launch's input
+    long long T0;            // stages since init when the launch starts
+    int npasses;             // 8-stage passes to run
+    int force_careful;
+};
+
 struct SingleArgs {
     Ctl *ctl;
-    uint16_t *metrics[2];
+    uint16_t *metrics[NBUF];
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;
@@ -35,6 +49,7 @@ struct TraceArgs {
 
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
 cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
+cudaError_t launch_persist(const PersistArgs &a, cudaStream_t st);
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

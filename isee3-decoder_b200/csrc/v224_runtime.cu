@@ -88,7 +88,7 @@ struct Decoder {
     int dev;
     int len;
     cudaStream_t stream;
-    uint16_t *metrics[2];
+    uint16_t *metrics[NBUF];
     uint32_t *ring;
     size_t ring_bytes;
     uint8_t *row_fmt;
@@ -104,9 +104,9 @@ struct Decoder {
     int *d_flag;
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, chain_seg, chain_warm;
+    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm;
     // counters
-    unsigned long long launches, acs_launches_timed, chainback_redo;
+    unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     double acs_ms;
     int time_kernels;
 };
@@ -151,7 +151,8 @@ void destroy(Decoder *d)
     cudaSetDevice(d->dev);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
-    cudaFree(d->metrics[0]); cudaFree(d->metrics[1]); cudaFree(d->row_fmt); cudaFree(d->ctl);
+    for (int i = 0; i < NBUF; i++) cudaFree(d->metrics[i]);
+    cudaFree(d->row_fmt); cudaFree(d->ctl);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
     cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
@@ -189,15 +190,28 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
     while (pos < nbits) {
         const int end = std::min(nbits, pos + BATCH_STAGES);
         if (d->time_kernels) CU(cudaEventRecord(d->kev0, d->stream));
+        int passes_in_batch = 0;
         unsigned long long n = 0;
         int p = pos;
+        const bool fuse = !d->force_single && !d->force_sat;
+        if (fuse && !d->per_pass_launch && end - p >= FK) {
+            // one persistent launch runs all full passes of this batch as a dataflow
+            const int npasses = (end - p) / FK;
+            PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p,
+                          d->h_ctl->cur, d->h_ctl->T, npasses, d->force_careful};
+            CU(launch_persist(a, d->stream));
+            p += npasses * FK;
+            n += 2;
+            passes_in_batch = npasses;
+        }
         while (p < end) {
-            if (!d->force_single && !d->force_sat && end - p >= FK) {
-                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, p, d->force_careful};
+            if (fuse && d->per_pass_launch && end - p >= FK) {
+                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, d->force_careful};
                 CU(launch_fused(a, d->stream));
                 p += FK;
+                passes_in_batch++;
             } else {
-                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, p, arg_s0 >= 0, arg_s0, arg_s1};
+                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, arg_s0 >= 0, arg_s0, arg_s1};
                 CU(launch_single(a, d->force_sat != 0, d->stream));
                 p += 1;
             }
@@ -211,12 +225,13 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
             CU(cudaEventElapsedTime(&ms, d->kev0, d->kev1));
             d->acs_ms += ms;
             d->acs_launches_timed += n;
+            d->acs_passes_timed += passes_in_batch;
         }
         if (d->h_ctl->pos >= end) { pos = end; continue; }
         // A pass declined to run: the reference's metrics are within 510*k of int16 saturation.
         // Do that stage with the exact saturating kernel and carry on from there.
         pos = d->h_ctl->pos;
-        SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1]}, d->ring, d->row_fmt, dev_syms, d->len, pos, arg_s0 >= 0, arg_s0, arg_s1};
+        SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, pos, arg_s0 >= 0, arg_s0, arg_s1};
         CU(launch_single(a, true, d->stream));
         d->launches++;
         if (sync_ctl(d)) return -1;
@@ -275,8 +290,7 @@ void *create_viterbi224(int len)
     d->ring_bytes = (size_t)len * ROWBYTES;
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&d->metrics[0], METRICBYTES) == cudaSuccess;
-    ok = ok && cudaMalloc(&d->metrics[1], METRICBYTES) == cudaSuccess;
+    for (int i = 0; i < NBUF; i++) ok = ok && cudaMalloc(&d->metrics[i], METRICBYTES) == cudaSuccess;
     ok = ok && cudaMalloc(&d->row_fmt, (size_t)len) == cudaSuccess;
     ok = ok && cudaMalloc(&d->ctl, sizeof(Ctl)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->d_redo, sizeof(unsigned)) == cudaSuccess;
@@ -519,7 +533,7 @@ int v224x_kernel_time_reset(void *p)
 {
     Decoder *d = as_dec(p);
     if (!d) return -1;
-    d->acs_ms = 0; d->acs_launches_timed = 0;
+    d->acs_ms = 0; d->acs_launches_timed = 0; d->acs_passes_timed = 0;
     return 0;
 }
 int v224x_kernel_time_enable(void *p, int on)
@@ -536,6 +550,11 @@ float v224x_kernel_time_ms(void *p, unsigned long long *n_acs_launches)
     if (n_acs_launches) *n_acs_launches = d->acs_launches_timed;
     return (float)d->acs_ms;
 }
+unsigned long long v224x_kernel_time_passes(void *p)
+{
+    Decoder *d = as_dec(p);
+    return d ? d->acs_passes_timed : 0;
+}
 
 int v224x_get_stats(void *p, v224x_stats *out)
 {
@@ -550,6 +569,7 @@ int v224x_get_stats(void *p, v224x_stats *out)
     out->careful_passes = d->h_ctl->n_careful;
     out->single_stages = d->h_ctl->n_single;
     out->sat_stages = d->h_ctl->n_sat;
+    out->invalidated_passes = d->h_ctl->n_invalidated;
     out->chainback_redo = redo;
     out->renormals = d->h_ctl->renormals;
     out->stages = d->h_ctl->T;
@@ -620,6 +640,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     if (!strcmp(key, "force_single")) d->force_single = (int)value;
     else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
+    else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

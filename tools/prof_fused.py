@@ -10,5 +10,5 @@ with v224.Viterbi224(n) as d:
     d.init(0)
     d.kernel_time_enable(True)
     d.update_blk(syms, n)
-    ms, k = d.kernel_time_ms()
-    print(f"{k} launches, {1e3 * ms / k:.2f} us per launch", d.stats())
+    ms, k, passes = d.kernel_time_ms()
+    print(f"{k} launches, {passes} passes, {1e3 * ms / passes:.2f} us per pass", d.stats())
