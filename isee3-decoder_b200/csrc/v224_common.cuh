@@ -30,9 +30,20 @@ constexpr long long MAX_FAST_SPREAD = 24000;
 // Fused pass geometry: FK stages per HBM pass, done as two register rounds of FR stages.
 constexpr int FR = 4;
 constexpr int FK = 2 * FR;                         // 8 trellis stages per pass
-constexpr int FUSED_TILE_COLS = 64;                // columns (j) per tile
-constexpr int FUSED_THREADS   = 128;               // 16 row-groups x 8 column groups
-constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512
+// Tile width.  64 columns (512 tiles of 128 threads, 4 CTAs/SM) measured 17.3 us per pass on B200,
+// 32 columns (1024 tiles of 64 threads, 8 CTAs/SM: better balanced, 7 vs 6 tiles per SM) 19.2 us:
+// the finer tiles lose more to per-tile overhead than they gain in balance (profiles/).
+#ifndef V224_TILE_COLS_LOG2
+#define V224_TILE_COLS_LOG2 6
+#endif
+constexpr int FUSED_COLS_LOG2 = V224_TILE_COLS_LOG2;
+constexpr int FUSED_TILE_COLS = 1 << FUSED_COLS_LOG2;  // columns (j) per tile
+constexpr int FUSED_COLGROUPS = FUSED_TILE_COLS / 8;   // 8 columns (4 packed registers) per thread
+constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column groups
+constexpr int FUSED_CTAS_PER_SM = 512 / FUSED_THREADS; // 16 warps per SM at 128 registers
+constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // tiles per pass
+constexpr int TILE_CLASSES    = 128 / FUSED_TILE_COLS; // tile t of pass n+1 reads the tiles == (t >> 8) mod TILE_CLASSES of pass n
+static_assert(FUSED_TILE_COLS == 32 || FUSED_TILE_COLS == 64, "tile width");
 
 // Path-metric buffers rotate A -> B -> C -> A.  Three (not two) so that, in the persistent kernel,
 // pass n+1 may already be writing while pass n is still being validated: pass n's input stays
@@ -58,13 +69,13 @@ struct PassSlot {
     unsigned s0[FK + 1];    // P of state 0 after stage t
     unsigned minP[FK + 1];  // global min of P after stage t ([FK] always, the others in careful passes)
     unsigned maxP;          // global max of P after the last stage
-    unsigned done[2];       // finished tiles by parity of the tile index (what the next pass waits on)
+    unsigned done[TILE_CLASSES];   // finished tiles by (tile index mod TILE_CLASSES): what the next pass waits on
     unsigned done_total;
     int sub;                // what this pass subtracts from every P while loading
     int careful;            // this pass records per-stage minima
 };
 struct PersistCtl {
-    unsigned next_item;     // work queue head: item = pass * 512 + order index
+    unsigned next_item;     // dynamic work queue head: item = pass * 512 + order index
     unsigned resolved_upto; // number of passes resolved (in order)
     int stop_pass;          // passes >= stop_pass must not run (saturation watch / invalidated pass)
     int npasses;
@@ -98,16 +109,17 @@ struct Ctl {
 };
 
 // where a fused-format decision bit lives: stage t (1..FK), state s after that stage.
-// Returns the bit index inside the 2^23-bit row.
+// Returns the bit index inside the 2^23-bit row.  Slot fields (23 bits):
+//   mh[4] | ml[4] | tile | g | q[2] | h[1]      (tile: 9 or 10 bits, g: 3 or 2 bits)
 __host__ __device__ inline uint32_t fused_bit_address(int t, uint32_t s)
 {
-    // slot p = state rotated right by t (the slot that held the state's ancestor tile position)
+    // slot p = state rotated right by t (the slot its survivor sits in during the pass)
     uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;
-    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, tau = (p >> 6) & 511, g = (p >> 3) & 7;
+    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, tile = (p >> FUSED_COLS_LOG2) & (FUSED_TILES - 1), g = (p >> 3) & (FUSED_COLGROUPS - 1);
     uint32_t q = (p >> 1) & 3, h = p & 1;
     uint32_t thr   = (t <= FR) ? ml : mh;       // thread row-group in this round
     uint32_t inner = (t <= FR) ? mh : ml;       // register row index in this round
-    uint32_t chunk = tau * FUSED_THREADS + thr * 8 + g;          // 16-byte chunk per thread
+    uint32_t chunk = tile * FUSED_THREADS + thr * FUSED_COLGROUPS + g;   // 16-byte chunk per thread
     uint32_t w     = inner >> 2;                                  // word in chunk
     uint32_t i     = ((inner & 3) << 1) | (q >> 1);               // bit in byte
     uint32_t byte  = ((q & 1) << 1) | h;                          // byte in word

@@ -14,8 +14,24 @@
 #include "v224_common.cuh"
 #include "v224_fused_core.cuh"
 #include "v224_kernels.h"
+#include <cstdio>
 
 namespace v224 {
+
+#ifdef V224_TRACE
+__device__ unsigned long long g_trace[64 * 1024 * 8];      // [pass < 64][tile][event]
+__device__ unsigned g_smid[64 * 1024];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(n, tau, ev) do { if (threadIdx.x == 0 && (n) < 64) { g_trace[((n) * 1024 + (tau)) * 8 + (ev)] = gtime(); if ((ev) == 1) { unsigned sm_; asm volatile("mov.u32 %0, %smid;" : "=r"(sm_)); g_smid[(n) * 1024 + (tau)] = sm_; } } } while (0)
+#else
+#define TRACE(n, tau, ev) do { } while (0)
+#endif
+
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -104,9 +120,16 @@ __global__ void __launch_bounds__(256) k_init(uint16_t *m0, Ctl *c, uint32_t sta
 // fused 8-stage pass
 // ------------------------------------------------------------------------------------------
 struct __align__(16) FusedSmem {
-    uint32_t tile[256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 = 32 KiB
+    uint32_t tile[256 * FUSED_TILE_COLS / 2];   // 256 rows x FUSED_TILE_COLS columns of uint16 (32 / 16 KiB)
     uint32_t optab[OPTAB_WORDS];                 // 1 KiB
 };
+
+// Operand tables of a whole launch: one 1 KiB table per pass, from that pass's 8 symbol pairs.
+__global__ void __launch_bounds__(256) k_build_optab(uint32_t *optab, const uint8_t *syms, int npasses)
+{
+    const int pass = blockIdx.x;
+    if (pass < npasses) optab[(size_t)pass * OPTAB_WORDS + threadIdx.x] = optab_entry(threadIdx.x, syms + 2 * (size_t)pass * FK);
+}
 
 template <int T>
 __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t *ring, uint8_t *row_fmt,
@@ -129,16 +152,19 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase
 // The body shared by the per-pass kernel and the persistent kernel: one tile, eight stages.
 // LDCG: metrics are read through L2 only (another SM wrote them, possibly within this launch).
 __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, uint16_t *newm, uint32_t *ring, uint8_t *row_fmt, int len,
-                                           const uint8_t *sym, unsigned *s0, unsigned *minP, unsigned *maxP, long long T0, uint32_t sub,
-                                           bool careful, uint32_t tau)
+                                           const uint32_t *optab_g, unsigned *s0, unsigned *minP, unsigned *maxP, long long T0, uint32_t sub,
+                                           bool careful, uint32_t tau, int trace_n = 1 << 30)
 {
     const uint32_t tid = threadIdx.x;
-    const uint32_t thr = tid >> 3, g = tid & 7;                    // row group, column group
+    const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS;   // row group (16), column group (4 x 8 columns)
     const uint32_t chunk = tau * FUSED_THREADS + tid;
     const bool first = tau == 0 && tid == 0;
 
-    // operand table for the 8 symbol pairs of this pass
-    for (int e = tid; e < OPTAB_WORDS; e += FUSED_THREADS) sm.optab[e] = optab_entry(e, sym);
+    // operand table of this pass (precomputed by k_build_optab): 1 KiB -> shared memory.  The persistent
+    // kernel fetches it before it waits for the previous pass (optab_g == nullptr here).
+    if (optab_g != nullptr)
+        for (int e = tid; e < OPTAB_WORDS / 4; e += FUSED_THREADS)
+            reinterpret_cast<uint4 *>(sm.optab)[e] = __ldcg(reinterpret_cast<const uint4 *>(optab_g) + e);
 
     // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 8 columns ----
     uint32_t A[16][4];
@@ -151,33 +177,45 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
         }
     }
     __syncthreads();                                               // optab ready
+#ifdef V224_TRACE
+    if (tid == 0 && trace_n < 64) { unsigned keep = A[0][0] ^ A[15][3]; if (keep == 0x12345678u) g_trace[0] = 0; g_trace[(trace_n * 1024 + tau) * 8 + 2] = gtime(); }
+#endif
     {
-        const uint32_t pbase = (thr << 15) | (tau << 6) | (g << 3);
+        const uint32_t pbase = (thr << 15) | (tau << FUSED_COLS_LOG2) | (g << 3);
         fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
     }
-    // ---- exchange: rows m = mh*16 + ml, 128 B per row ----
+    // ---- exchange: rows m = mh*16 + ml; element (row, g) at 16-byte index row*COLGROUPS + g.  With 4 column groups
+    // (64 B rows) the index is XORed with (mh & 1) << 2 so that round 2's stride-16-row reads hit distinct bank groups;
+    // with 8 column groups a quarter-warp reads one whole 128 B row and needs no swizzle. ----
     {
         uint4 *t4 = reinterpret_cast<uint4 *>(sm.tile);
 #pragma unroll
-        for (int mh = 0; mh < 16; mh++) t4[(mh * 16 + thr) * 8 + g] = make_uint4(A[mh][0], A[mh][1], A[mh][2], A[mh][3]);
+        for (int mh = 0; mh < 16; mh++)
+            t4[((mh * 16 + thr) * FUSED_COLGROUPS + g) ^ (FUSED_COLGROUPS == 4 ? (mh & 1) << 2 : 0)] = make_uint4(A[mh][0], A[mh][1], A[mh][2], A[mh][3]);
         __syncthreads();
 #pragma unroll
         for (int ml = 0; ml < 16; ml++) {
-            const uint4 v = t4[(thr * 16 + ml) * 8 + g];
+            const uint4 v = t4[((thr * 16 + ml) * FUSED_COLGROUPS + g) ^ (FUSED_COLGROUPS == 4 ? (thr & 1) << 2 : 0)];
             A[ml][0] = v.x; A[ml][1] = v.y; A[ml][2] = v.z; A[ml][3] = v.w;
         }
     }
+#ifdef V224_TRACE
+    if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + tau) * 8 + 3] = gtime();
+#endif
     // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
     {
-        const uint32_t pbase = (thr << 19) | (tau << 6) | (g << 3);
+        const uint32_t pbase = (thr << 19) | (tau << FUSED_COLS_LOG2) | (g << 3);
         fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
         fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
     }
+#ifdef V224_TRACE
+    if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + tau) * 8 + 4] = gtime();
+#endif
     // ---- statistics of the final stage ----
     {
         const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
@@ -200,7 +238,7 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_fused(FusedArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
@@ -210,7 +248,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_fused(FusedArgs a)
     if (c->pos != a.expected_pos || c->error) return;
     if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
     const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
-    fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.syms + 2 * (size_t)a.expected_pos,
+    fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.optab,
                c->s0, c->minP, &c->maxP_end, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x);
 
     // ---- last CTA resolves the pass ----
@@ -253,11 +291,11 @@ __device__ __forceinline__ void slot_reset(PassSlot &s)
 #pragma unroll
     for (int t = 0; t <= FK; t++) { s.s0[t] = 0; s.minP[t] = 0xffffffffu; }
     s.maxP = 0;
-    s.done[0] = s.done[1] = 0;
+    for (int k = 0; k < TILE_CLASSES; k++) s.done[k] = 0;
     s.done_total = 0;
 }
 
-__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful)
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, int expected_pos)
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
@@ -272,7 +310,7 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful)
     pc.slot[0].careful = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     pc.slot[1].careful = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
     int stop = npasses;
-    if (c->spread > MAX_FAST_SPREAD || c->error) stop = 0;
+    if (c->spread > MAX_FAST_SPREAD || c->error || c->pos != expected_pos) stop = 0;
     // non-careful passes are not validated stage by stage: keep them well away from saturation
     if (!pc.slot[0].careful && c->maxR + 510ll * FK > 32767) stop = 0;
     if (stop > 1 && !pc.slot[1].careful && c->maxR + 510ll * 2 * FK > 32767) stop = 1;
@@ -342,55 +380,80 @@ __device__ void resolve_persist(Ctl *c, int n)
     st_release(&pc.resolved_upto, (unsigned)(n + 1));
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 4) k_acs_persist(PersistArgs a)
+__device__ __forceinline__ unsigned ld_relaxed(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Work distribution.  STATIC: CTA b owns tile b in every pass; all FUSED_TILES CTAs must be co-resident
+// (16 warps per SM x 148 SMs hold 592 / 1184 CTAs of 128 / 64 threads), so the kernel is launched cooperatively and the driver refuses
+// instead of deadlocking.  Dynamic: CTAs take (pass, tile) items from an atomic queue in pass-major
+// order, even tiles first; nothing has to be co-resident because only running CTAs hold items.
+template <bool STATIC>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persist(PersistArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
     Ctl *c = a.ctl;
     PersistCtl &pc = c->pc;
+    __shared__ int s_go, s_sub, s_careful;
     __shared__ unsigned s_item;
-    __shared__ int s_go, s_sub, s_careful, s_cur;
-    __shared__ long long s_T;
     const uint32_t tid = threadIdx.x;
 
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(&pc.next_item, 1u);
-        __syncthreads();
-        const unsigned item = s_item;
-        const int n = (int)(item >> 9);
+    for (int k = 0;; k++) {
+        int n;
+        uint32_t tau;
+        if (STATIC) {
+            n = k;
+            tau = blockIdx.x;
+        } else {
+            if (tid == 0) s_item = atomicAdd(&pc.next_item, 1u);
+            __syncthreads();
+            const unsigned item = s_item;
+            n = (int)(item / FUSED_TILES);
+            const unsigned w = item % FUSED_TILES;                             // a pass emits its tile classes in turn
+            tau = (w % 256u) * TILE_CLASSES + w / 256u;
+        }
         if (n >= a.npasses) break;
-        // even tiles of a pass first (the next pass's first half waits only for them)
-        const unsigned w = item & 511u, cls = w >> 7, idx = w & 127u;
-        const uint32_t tau = ((cls & 1u) << 8) | (idx << 1) | (cls >> 1);
+        TRACE(n, tau, 0);
         PassSlot &sl = pc.slot[n % PSLOTS];
+        // Everything that does not depend on the previous pass's data is fetched BEFORE waiting for it:
+        // the operand table (symbols are known) and the pass parameters (published two passes ago).
+        for (int e = tid; e < OPTAB_WORDS / 4; e += FUSED_THREADS)
+            reinterpret_cast<uint4 *>(sm.optab)[e] = __ldcg(reinterpret_cast<const uint4 *>(a.optab + (size_t)n * OPTAB_WORDS) + e);
         if (tid == 0) {
-            while ((int)ld_acquire(&pc.resolved_upto) < n - 1) __nanosleep(100);      // parameters of pass n exist
-            int go = n < *(volatile int *)&pc.stop_pass;
+            while ((int)ld_relaxed(&pc.resolved_upto) < n - 1) __nanosleep(200);      // parameters of pass n exist
+            s_sub = (int)ld_relaxed(&sl.sub);
+            s_careful = (int)ld_relaxed(&sl.careful);
+            int go = n < (int)ld_relaxed(&pc.stop_pass);
             if (go && n > 0) {
+                // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
                 const unsigned *dep = &pc.slot[(n - 1) % PSLOTS].done[tau >> 8];
+                unsigned spins = 0;
                 while (ld_acquire(dep) < 256u) {
-                    __nanosleep(40);
-                    if (n >= *(volatile int *)&pc.stop_pass) { go = 0; break; }
+                    __nanosleep(32);
+                    if ((++spins & 15u) == 0 && n >= (int)ld_relaxed(&pc.stop_pass)) { go = 0; break; }
                 }
             }
             s_go = go;
-            s_sub = *(volatile int *)&sl.sub;
-            s_careful = *(volatile int *)&sl.careful;
-            // the first pass of the launch starts from the control block's buffer / stage counter;
-            // both advance by one per resolved pass, so pass n is at a fixed offset from the launch state
-            s_cur = a.cur0;
-            s_T = a.T0;
         }
         __syncthreads();
         if (!s_go) break;
-        const int cur = (s_cur + n) % NBUF;
-        fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.syms + 2 * ((size_t)a.pos0 + (size_t)n * FK),
-                   sl.s0, sl.minP, &sl.maxP, s_T + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, tau);
+        TRACE(n, tau, 1);
+        // buffer and stage counter advance by one per resolved pass: pass n sits at a fixed offset from the launch state
+        const int cur = (a.cur0 + n) % NBUF;
+        fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, nullptr,
+                   sl.s0, sl.minP, &sl.maxP, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, tau, n);
         __syncthreads();                       // every thread's stores and statistics are issued
+        TRACE(n, tau, 5);
         if (tid == 0) {
             __threadfence();                   // ... and visible GPU-wide before the tile counts as done
-            atomicAdd(&sl.done[tau & 1u], 1u);
+            TRACE(n, tau, 6);
+            atomicAdd(&sl.done[tau % TILE_CLASSES], 1u);
             if (atomicAdd(&sl.done_total, 1u) == FUSED_TILES - 1) resolve_persist(c, n);
+            TRACE(n, tau, 7);
         }
     }
 }
@@ -678,30 +741,45 @@ cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st)
         if (e != cudaSuccess) return e;
         g_fused_attr_set[dev] = true;
     }
+    k_build_optab<<<1, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.expected_pos, 1);
     k_acs_fused<<<FUSED_TILES, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_persist(const PersistArgs &a, cudaStream_t st)
+cudaError_t launch_persist(const PersistArgs &a, bool static_tiles, cudaStream_t st)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool attr_set[64];
-    static int grid_cap[64];
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    static int checked[64], slots[64];
+    if (dev >= 0 && dev < 64 && !checked[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_acs_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        // 4 x 33 KiB or 8 x 17 KiB (+1 KiB reserved each) per SM: ask for the large shared-memory carve-out
+        cudaFuncSetAttribute(k_acs_persist<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_acs_persist<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_acs_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, FUSED_THREADS, sizeof(FusedSmem));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist<true>, FUSED_THREADS, sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        grid_cap[dev] = per_sm * sms;
-        attr_set[dev] = true;
+        slots[dev] = per_sm * sms;
+        checked[dev] = 1;
     }
-    k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful);
+    k_build_optab<<<a.npasses, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.pos0, a.npasses);
+    k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful, a.pos0);
+    if (static_tiles) {
+        if (slots[dev] < FUSED_TILES) {
+            fprintf(stderr, "[viterbi224_b200] static tiles need %d co-resident CTAs, the device holds %d\n", FUSED_TILES, slots[dev]);
+            return cudaErrorCooperativeLaunchTooLarge;
+        }
+        PersistArgs args = a;
+        void *params[] = {&args};
+        return cudaLaunchCooperativeKernel((const void *)k_acs_persist<true>, dim3(FUSED_TILES), dim3(FUSED_THREADS), params, sizeof(FusedSmem), st);
+    }
     const long long items = (long long)a.npasses * FUSED_TILES;
-    const int grid = (int)(items < grid_cap[dev] ? items : grid_cap[dev]);
-    k_acs_persist<<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+    const int grid = (int)(items < slots[dev] ? items : slots[dev]);
+    k_acs_persist<false><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)
@@ -765,3 +843,14 @@ cudaError_t launch_import_metrics(uint16_t *m, const int16_t *in, Ctl *c, unsign
 }
 
 } // namespace v224
+
+#ifdef V224_TRACE
+extern "C" int v224_debug_read_trace(unsigned long long *host, unsigned long long n)
+{
+    return (int)cudaMemcpyFromSymbol(host, v224::g_trace, n * sizeof(unsigned long long));
+}
+extern "C" int v224_debug_read_smid(unsigned *host, unsigned long long n)
+{
+    return (int)cudaMemcpyFromSymbol(host, v224::g_smid, n * sizeof(unsigned));
+}
+#endif

@@ -10,6 +10,7 @@ struct FusedArgs {
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;     // device symbols of the running update call (2 per bit)
+    uint32_t *optab;         // scratch: this pass's operand table (256 words)
     int len;                 // ring rows
     int expected_pos;        // stages of this call that must already be done
     int force_careful;       // test knob: record per-stage minima regardless
@@ -21,6 +22,7 @@ struct PersistArgs {
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;     // symbols of the running update call; this launch starts at stage pos0
+    uint32_t *optab;         // npasses x 256 words, filled by k_build_optab at launch
     int len;
     int pos0;                // stages of this call already done when the launch starts
     int cur0;                // metric buffer holding the launch's input
@@ -49,7 +51,7 @@ struct TraceArgs {
 
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
 cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
-cudaError_t launch_persist(const PersistArgs &a, cudaStream_t st);
+cudaError_t launch_persist(const PersistArgs &a, bool static_tiles, cudaStream_t st);
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

@@ -95,6 +95,7 @@ struct Decoder {
     Ctl *ctl;
     Ctl *h_ctl;                 // pinned mirror, refreshed at the end of every update
     uint8_t *dsyms; size_t dsyms_cap;
+    uint32_t *optab; size_t optab_cap;     // per-pass operand tables of the running batch
     uint8_t *dout;  size_t dout_cap;       // chainback / stream output staging
     uint32_t *seg;  size_t seg_cap;        // chainback segment bookkeeping
     unsigned *d_redo;
@@ -104,7 +105,7 @@ struct Decoder {
     int *d_flag;
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm;
+    int force_single, force_sat, force_careful, per_pass_launch, static_tiles, chain_seg, chain_warm;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     double acs_ms;
@@ -153,6 +154,7 @@ void destroy(Decoder *d)
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
     for (int i = 0; i < NBUF; i++) cudaFree(d->metrics[i]);
     cudaFree(d->row_fmt); cudaFree(d->ctl);
+    cudaFree(d->optab);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
     cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
@@ -197,17 +199,20 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         if (fuse && !d->per_pass_launch && end - p >= FK) {
             // one persistent launch runs all full passes of this batch as a dataflow
             const int npasses = (end - p) / FK;
-            PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p,
+            if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
+            PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
                           d->h_ctl->cur, d->h_ctl->T, npasses, d->force_careful};
-            CU(launch_persist(a, d->stream));
+            CU(launch_persist(a, d->static_tiles != 0, d->stream));
             p += npasses * FK;
-            n += 2;
+            n += 3;
             passes_in_batch = npasses;
         }
         while (p < end) {
             if (fuse && d->per_pass_launch && end - p >= FK) {
-                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, d->force_careful};
+                if (grow((void **)&d->optab, &d->optab_cap, 1024)) return -1;
+                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p, d->force_careful};
                 CU(launch_fused(a, d->stream));
+                n++;
                 p += FK;
                 passes_in_batch++;
             } else {
@@ -641,6 +646,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
+    else if (!strcmp(key, "static_tiles")) d->static_tiles = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

@@ -40,28 +40,28 @@ void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const 
     for (uint32_t tau = 0; tau < FUSED_TILES; tau++) {
         // round 1
         for (uint32_t tid = 0; tid < FUSED_THREADS; tid++) {
-            const uint32_t thr = tid >> 3, g = tid & 7, chunk = tau * FUSED_THREADS + tid;
+            const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS, chunk = tau * FUSED_THREADS + tid;
             uint32_t A[16][4];
             for (int mh = 0; mh < 16; mh++) {
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(oldP + ((size_t)(mh * 16 + thr) * 32768 + tau * FUSED_TILE_COLS + g * 8));
                 for (int q = 0; q < 4; q++) A[mh][q] = src[q] - sub2;
             }
-            const uint32_t pbase = (thr << 15) | (tau << 6) | (g << 3);
+            const uint32_t pbase = (thr << 15) | (tau << FUSED_COLS_LOG2) | (g << 3);
             const bool first = tau == 0 && tid == 0;
             emu_stage<1>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
             emu_stage<2>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
             emu_stage<3>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
             emu_stage<4>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
             for (int mh = 0; mh < 16; mh++)
-                for (int q = 0; q < 4; q++) tile[((mh * 16 + thr) * 8 + g) * 4 + q] = A[mh][q];
+                for (int q = 0; q < 4; q++) tile[((mh * 16 + thr) * FUSED_COLGROUPS + g) * 4 + q] = A[mh][q];
         }
         // round 2
         for (uint32_t tid = 0; tid < FUSED_THREADS; tid++) {
-            const uint32_t thr = tid >> 3, g = tid & 7, chunk = tau * FUSED_THREADS + tid;
+            const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS, chunk = tau * FUSED_THREADS + tid;
             uint32_t A[16][4];
             for (int ml = 0; ml < 16; ml++)
-                for (int q = 0; q < 4; q++) A[ml][q] = tile[((thr * 16 + ml) * 8 + g) * 4 + q];
-            const uint32_t pbase = (thr << 19) | (tau << 6) | (g << 3);
+                for (int q = 0; q < 4; q++) A[ml][q] = tile[((thr * 16 + ml) * FUSED_COLGROUPS + g) * 4 + q];
+            const uint32_t pbase = (thr << 19) | (tau << FUSED_COLS_LOG2) | (g << 3);
             const bool first = tau == 0 && tid == 0;
             emu_stage<5>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
             emu_stage<6>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
