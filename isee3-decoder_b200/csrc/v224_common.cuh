@@ -52,7 +52,7 @@ constexpr int NBUF = 3;
 constexpr int PSLOTS = 4;                          // in-flight pass bookkeeping slots (ring)
 
 // Decision-row formats (row_fmt[] tags).  0 = canonical (bit index = new-state number, the
-// reference's layout, viterbi224_sse2.c:141,324); t in 1..FK = written by stage t of a fused
+// reference's layout, viterbi224_sse2.c:141,324); other values = written by a stage of a fused
 // pass in that kernel's thread-major layout (see fused_bit_address()).
 constexpr uint8_t ROWFMT_CANON = 0;
 
@@ -76,6 +76,9 @@ struct PassSlot {
 };
 struct PersistCtl {
     unsigned next_item;     // dynamic work queue head: item = pass * 512 + order index
+    unsigned next_rank;     // balanced mode: SM ranks handed out in arrival order
+    int sm_rank[256];       // balanced mode: rank of SM %smid (-1 until its first CTA arrives)
+    unsigned sm_slots[256]; // balanced mode: CTAs that arrived on SM %smid
     unsigned resolved_upto; // number of passes resolved (in order)
     int stop_pass;          // passes >= stop_pass must not run (saturation watch / invalidated pass)
     int npasses;
@@ -108,18 +111,46 @@ struct Ctl {
     PersistCtl pc;
 };
 
-// where a fused-format decision bit lives: stage t (1..FK), state s after that stage.
-// Returns the bit index inside the 2^23-bit row.  Slot fields (23 bits):
-//   mh[4] | ml[4] | tile | g | q[2] | h[1]      (tile: 9 or 10 bits, g: 3 or 2 bits)
-__host__ __device__ inline uint32_t fused_bit_address(int t, uint32_t s)
+// ---- tile partitions of the 4096 column groups (8 columns each) -------------------------------
+// UNIFORM: tile t = groups [t*CG, (t+1)*CG), CG = FUSED_COLGROUPS.
+// BALANCED (B200, 148 SMs x 4 CTAs): every SM gets 14 or 13 warps' worth of work instead of 16 or 12:
+//   SM rank r < 124 owns 28 consecutive groups as tiles of 8,8,6,6; rank r >= 124 owns 26 as 8,6,6,6
+//   (124*28 + 24*26 = 4096).  A tile of 6 groups uses 3 warps of its CTA, one of 8 groups all 4.
+constexpr int BAL_SMS = 148, BAL_CTAS_PER_SM = 4, BAL_BIG_SMS = 124, BAL_TILES = BAL_SMS * BAL_CTAS_PER_SM;
+__host__ __device__ inline void balanced_tile(uint32_t rank, uint32_t slot, uint32_t &g0, uint32_t &ncg)
 {
+    const bool big = rank < BAL_BIG_SMS;
+    const uint32_t base = big ? rank * 28u : BAL_BIG_SMS * 28u + (rank - BAL_BIG_SMS) * 26u;
+    if (big) { ncg = slot < 2 ? 8u : 6u; g0 = base + (slot < 2 ? slot * 8u : 16u + (slot - 2) * 6u); }
+    else     { ncg = slot < 1 ? 8u : 6u; g0 = base + (slot < 1 ? 0u : 8u + (slot - 1) * 6u); }
+}
+// the balanced tile that contains column group G
+__host__ __device__ inline void balanced_tile_of_group(uint32_t G, uint32_t &g0, uint32_t &ncg)
+{
+    uint32_t rank, r;
+    if (G < BAL_BIG_SMS * 28u) { rank = G / 28u; r = G % 28u; balanced_tile(rank, r < 8 ? 0 : r < 16 ? 1 : r < 22 ? 2 : 3, g0, ncg); }
+    else { const uint32_t Gp = G - BAL_BIG_SMS * 28u; rank = BAL_BIG_SMS + Gp / 26u; r = Gp % 26u; balanced_tile(rank, r < 8 ? 0 : r < 14 ? 1 : r < 20 ? 2 : 3, g0, ncg); }
+}
+
+// Decision-row formats: 0 = canonical; t (1..8) = stage t of a pass over UNIFORM tiles; 8 + t = over BALANCED tiles.
+constexpr uint8_t ROWFMT_BALANCED = 8;
+
+// where a fused-format decision bit lives: fmt as above, state s after that stage.
+// Returns the bit index inside the 2^23-bit row.  Slot fields (23 bits): mh[4] | ml[4] | G[12] | q[2] | h[1];
+// a thread (row group thr, column group G) of tile (g0, ncg) owns the 16-byte chunk g0*16 + thr*ncg + (G - g0).
+__host__ __device__ inline uint32_t fused_bit_address(int fmt, uint32_t s)
+{
+    const int t = fmt > ROWFMT_BALANCED ? fmt - ROWFMT_BALANCED : fmt;
     // slot p = state rotated right by t (the slot its survivor sits in during the pass)
     uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;
-    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, tile = (p >> FUSED_COLS_LOG2) & (FUSED_TILES - 1), g = (p >> 3) & (FUSED_COLGROUPS - 1);
+    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, G = (p >> 3) & 4095;
     uint32_t q = (p >> 1) & 3, h = p & 1;
+    uint32_t g0, ncg;
+    if (fmt > ROWFMT_BALANCED) balanced_tile_of_group(G, g0, ncg);
+    else { ncg = FUSED_COLGROUPS; g0 = G - G % FUSED_COLGROUPS; }
     uint32_t thr   = (t <= FR) ? ml : mh;       // thread row-group in this round
     uint32_t inner = (t <= FR) ? mh : ml;       // register row index in this round
-    uint32_t chunk = tile * FUSED_THREADS + thr * FUSED_COLGROUPS + g;   // 16-byte chunk per thread
+    uint32_t chunk = g0 * 16 + thr * ncg + (G - g0);              // 16-byte chunk per thread
     uint32_t w     = inner >> 2;                                  // word in chunk
     uint32_t i     = ((inner & 3) << 1) | (q >> 1);               // bit in byte
     uint32_t byte  = ((q & 1) << 1) | h;                          // byte in word

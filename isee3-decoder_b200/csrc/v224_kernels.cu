@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) k_build_optab(uint32_t *optab, const uint
 
 template <int T>
 __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t *ring, uint8_t *row_fmt,
-                                            int len, unsigned *s0, unsigned *minP, long long T0, bool careful, bool first, uint32_t chunk)
+                                            int len, unsigned *s0, unsigned *minP, long long T0, bool careful, bool first, uint32_t chunk,
+                                            int fmt_base)
 {
     uint32_t dw[4];
     acs_stage<T>(A, pbase, optab, dw);
@@ -141,7 +142,7 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase
     st_cs_v4(reinterpret_cast<uint8_t *>(ring) + (size_t)row * ROWBYTES + (size_t)chunk * 16, make_uint4(dw[0], dw[1], dw[2], dw[3]));
     if (first) {
         s0[T] = A[0][0] & 0xffffu;               // slot 0 always holds state 0
-        row_fmt[row] = (uint8_t)T;
+        row_fmt[row] = (uint8_t)(fmt_base + T);
     }
     if (careful && T < FK) {
         uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
@@ -150,15 +151,21 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase
 }
 
 // The body shared by the per-pass kernel and the persistent kernel: one tile, eight stages.
+// The tile is the column groups [g0, g0 + ncg) (8 columns each; ncg = 8, or 6 in the balanced partition);
+// thread tid = thr * ncg + g handles row group thr and column group g0 + g; threads >= 16 * ncg only keep
+// the CTA barriers company (a 6-group tile leaves its fourth warp idle).
 // LDCG: metrics are read through L2 only (another SM wrote them, possibly within this launch).
 __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, uint16_t *newm, uint32_t *ring, uint8_t *row_fmt, int len,
                                            const uint32_t *optab_g, unsigned *s0, unsigned *minP, unsigned *maxP, long long T0, uint32_t sub,
-                                           bool careful, uint32_t tau, int trace_n = 1 << 30)
+                                           bool careful, uint32_t g0, uint32_t ncg, int fmt_base, int trace_n = 1 << 30, uint32_t trace_id = 0)
 {
     const uint32_t tid = threadIdx.x;
-    const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS;   // row group (16), column group (4 x 8 columns)
-    const uint32_t chunk = tau * FUSED_THREADS + tid;
-    const bool first = tau == 0 && tid == 0;
+    const bool active = tid < 16u * ncg;
+    const uint32_t thr = tid / ncg, g = tid % ncg;                 // row group (16), column group within the tile
+    const uint32_t G = g0 + g;                                     // global column group: columns 8G .. 8G+7
+    const uint32_t chunk = g0 * 16u + tid;                         // = g0*16 + thr*ncg + g, see fused_bit_address()
+    const bool first = G == 0 && thr == 0;
+    uint4 *t4 = reinterpret_cast<uint4 *>(sm.tile);
 
     // operand table of this pass (precomputed by k_build_optab): 1 KiB -> shared memory.  The persistent
     // kernel fetches it before it waits for the previous pass (optab_g == nullptr here).
@@ -166,73 +173,68 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
         for (int e = tid; e < OPTAB_WORDS / 4; e += FUSED_THREADS)
             reinterpret_cast<uint4 *>(sm.optab)[e] = __ldcg(reinterpret_cast<const uint4 *>(optab_g) + e);
 
-    // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 8 columns ----
     uint32_t A[16][4];
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(oldm) + ((size_t)thr * 32768 + tau * FUSED_TILE_COLS + g * 8) / 8;
+    if (active) {
+        // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 8 columns ----
+        const uint4 *src = reinterpret_cast<const uint4 *>(oldm) + (size_t)thr * 4096 + G;
 #pragma unroll
         for (int mh = 0; mh < 16; mh++) {
-            const uint4 v = __ldcg(src + (size_t)mh * 16 * 32768 / 8);
+            const uint4 v = __ldcg(src + (size_t)mh * 16 * 4096);
             A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][2] = v.z - sub; A[mh][3] = v.w - sub;
         }
     }
     __syncthreads();                                               // optab ready
 #ifdef V224_TRACE
-    if (tid == 0 && trace_n < 64) { unsigned keep = A[0][0] ^ A[15][3]; if (keep == 0x12345678u) g_trace[0] = 0; g_trace[(trace_n * 1024 + tau) * 8 + 2] = gtime(); }
+    if (tid == 0 && trace_n < 64) { unsigned keep = A[0][0] ^ A[15][3]; if (keep == 0x12345678u) g_trace[0] = 0; g_trace[(trace_n * 1024 + trace_id) * 8 + 2] = gtime(); }
 #endif
-    {
-        const uint32_t pbase = (thr << 15) | (tau << FUSED_COLS_LOG2) | (g << 3);
-        fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-    }
-    // ---- exchange: rows m = mh*16 + ml; element (row, g) at 16-byte index row*COLGROUPS + g.  With 4 column groups
-    // (64 B rows) the index is XORed with (mh & 1) << 2 so that round 2's stride-16-row reads hit distinct bank groups;
-    // with 8 column groups a quarter-warp reads one whole 128 B row and needs no swizzle. ----
-    {
-        uint4 *t4 = reinterpret_cast<uint4 *>(sm.tile);
+    if (active) {
+        const uint32_t pbase = (thr << 15) | (G << 3);
+        fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        // ---- exchange: rows m = mh*16 + ml; element (row, g) at 16-byte index row*ncg + g.  A quarter-warp
+        // touches 8 consecutive 16-byte slots when ncg = 8 (conflict-free); ncg = 6 costs a few 2-way conflicts ----
 #pragma unroll
-        for (int mh = 0; mh < 16; mh++)
-            t4[((mh * 16 + thr) * FUSED_COLGROUPS + g) ^ (FUSED_COLGROUPS == 4 ? (mh & 1) << 2 : 0)] = make_uint4(A[mh][0], A[mh][1], A[mh][2], A[mh][3]);
-        __syncthreads();
+        for (int mh = 0; mh < 16; mh++) t4[(mh * 16 + thr) * ncg + g] = make_uint4(A[mh][0], A[mh][1], A[mh][2], A[mh][3]);
+    }
+    __syncthreads();
+    if (active) {
 #pragma unroll
         for (int ml = 0; ml < 16; ml++) {
-            const uint4 v = t4[((thr * 16 + ml) * FUSED_COLGROUPS + g) ^ (FUSED_COLGROUPS == 4 ? (thr & 1) << 2 : 0)];
+            const uint4 v = t4[(thr * 16 + ml) * ncg + g];
             A[ml][0] = v.x; A[ml][1] = v.y; A[ml][2] = v.z; A[ml][3] = v.w;
         }
-    }
 #ifdef V224_TRACE
-    if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + tau) * 8 + 3] = gtime();
+        if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + trace_id) * 8 + 3] = gtime();
 #endif
-    // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
-    {
-        const uint32_t pbase = (thr << 19) | (tau << FUSED_COLS_LOG2) | (g << 3);
-        fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-        fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk);
-    }
+        // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
+        const uint32_t pbase = (thr << 19) | (G << 3);
+        fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
 #ifdef V224_TRACE
-    if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + tau) * 8 + 4] = gtime();
+        if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + trace_id) * 8 + 4] = gtime();
 #endif
-    // ---- statistics of the final stage ----
-    {
-        const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
-        const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
-        if ((tid & 31) == 0) { atomicMin(&minP[FK], mn); atomicMax(maxP, mx); }
-    }
-    // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B ----
-    {
-        const uint32_t jbase = tau * FUSED_TILE_COLS + g * 8;
+        // ---- statistics of the final stage ----
+        {
+            const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
+            if ((tid & 31) == 0) { atomicMin(&minP[FK], mn); atomicMax(maxP, mx); }
+        }
+        // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B ----
+        {
+            const uint32_t jbase = G * 8;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 4; q++) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t w[8];
+                for (int h = 0; h < 2; h++) {
+                    uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) w[i] = __byte_perm(A[2 * i][q], A[2 * i + 1][q], h ? 0x7632 : 0x5410);
-                st_v8(newm + ((size_t)(jbase + q * 2 + h) << 8) + thr * 16, w);
+                    for (int i = 0; i < 8; i++) w[i] = __byte_perm(A[2 * i][q], A[2 * i + 1][q], h ? 0x7632 : 0x5410);
+                    st_v8(newm + ((size_t)(jbase + q * 2 + h) << 8) + thr * 16, w);
+                }
             }
         }
     }
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_fused(
     if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
     const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.optab,
-               c->s0, c->minP, &c->maxP_end, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x);
+               c->s0, c->minP, &c->maxP_end, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x * FUSED_COLGROUPS, FUSED_COLGROUPS, 0);
 
     // ---- last CTA resolves the pass ----
     __shared__ unsigned s_ticket;
@@ -299,6 +301,8 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, int expe
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
+    pc.next_rank = 0;
+    for (int i = 0; i < 256; i++) { pc.sm_rank[i] = -1; pc.sm_slots[i] = 0; }
     pc.resolved_upto = 0;
     pc.npasses = npasses;
     pc.force_careful = force_careful;
@@ -387,11 +391,17 @@ __device__ __forceinline__ unsigned ld_relaxed(const void *p)
     return v;
 }
 
-// Work distribution.  STATIC: CTA b owns tile b in every pass; all FUSED_TILES CTAs must be co-resident
-// (16 warps per SM x 148 SMs hold 592 / 1184 CTAs of 128 / 64 threads), so the kernel is launched cooperatively and the driver refuses
-// instead of deadlocking.  Dynamic: CTAs take (pass, tile) items from an atomic queue in pass-major
-// order, even tiles first; nothing has to be co-resident because only running CTAs hold items.
-template <bool STATIC>
+// Work distribution modes.
+//   DYNAMIC : CTAs take (pass, tile) items from an atomic queue in pass-major order, a pass's tile classes in turn.
+//             Nothing has to be co-resident because only running CTAs hold items.
+//   STATIC  : CTA b owns uniform tile b in every pass; all FUSED_TILES CTAs must be co-resident, so the kernel is
+//             launched cooperatively and the driver refuses instead of deadlocking.
+//   BALANCED: 592 CTAs = 148 SMs x 4.  Each CTA finds out which SM it landed on and takes one of that SM's four
+//             tiles of the balanced partition (8,8,6,6 or 8,6,6,6 column groups): every SM carries 14 or 13 warps
+//             of work per pass instead of 16 or 12.  Cooperative launch as well.
+enum { MODE_DYNAMIC = 0, MODE_STATIC = 1, MODE_BALANCED = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persist(PersistArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -399,22 +409,51 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persis
     Ctl *c = a.ctl;
     PersistCtl &pc = c->pc;
     __shared__ int s_go, s_sub, s_careful;
-    __shared__ unsigned s_item;
+    __shared__ unsigned s_item, s_g0, s_ncg;
     const uint32_t tid = threadIdx.x;
+    constexpr unsigned NTILES = MODE == MODE_BALANCED ? BAL_TILES : FUSED_TILES;
+    constexpr int FMT = MODE == MODE_BALANCED ? ROWFMT_BALANCED : 0;
+
+    if (MODE == MODE_BALANCED) {
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            smid &= 255u;
+            const unsigned slot = atomicAdd(&pc.sm_slots[smid], 1u);
+            int rank;
+            if (slot == 0) {
+                rank = (int)atomicAdd(&pc.next_rank, 1u);
+                st_release(reinterpret_cast<unsigned *>(&pc.sm_rank[smid]), (unsigned)rank);
+            } else {
+                while ((rank = (int)ld_acquire(reinterpret_cast<const unsigned *>(&pc.sm_rank[smid]))) < 0) __nanosleep(50);
+            }
+            uint32_t g0 = 0, ncg = 0;
+            if (rank < BAL_SMS && slot < (unsigned)BAL_CTAS_PER_SM) balanced_tile((uint32_t)rank, slot, g0, ncg);
+            else c->error |= 8;                                    // not 148 SMs x 4 CTAs: the host must not use this mode
+            s_g0 = g0;
+            s_ncg = ncg;
+        }
+        __syncthreads();
+        if (s_ncg == 0) return;
+    }
 
     for (int k = 0;; k++) {
         int n;
-        uint32_t tau;
-        if (STATIC) {
-            n = k;
-            tau = blockIdx.x;
-        } else {
+        uint32_t g0, ncg, tau;
+        if (MODE == MODE_DYNAMIC) {
             if (tid == 0) s_item = atomicAdd(&pc.next_item, 1u);
             __syncthreads();
             const unsigned item = s_item;
             n = (int)(item / FUSED_TILES);
             const unsigned w = item % FUSED_TILES;                             // a pass emits its tile classes in turn
             tau = (w % 256u) * TILE_CLASSES + w / 256u;
+            g0 = tau * FUSED_COLGROUPS; ncg = FUSED_COLGROUPS;
+        } else if (MODE == MODE_STATIC) {
+            n = k; tau = blockIdx.x;
+            g0 = tau * FUSED_COLGROUPS; ncg = FUSED_COLGROUPS;
+        } else {
+            n = k; tau = blockIdx.x;
+            g0 = s_g0; ncg = s_ncg;
         }
         if (n >= a.npasses) break;
         TRACE(n, tau, 0);
@@ -429,10 +468,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persis
             s_careful = (int)ld_relaxed(&sl.careful);
             int go = n < (int)ld_relaxed(&pc.stop_pass);
             if (go && n > 0) {
-                // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
-                const unsigned *dep = &pc.slot[(n - 1) % PSLOTS].done[tau >> 8];
+                // uniform tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass;
+                // balanced tiles do not line up with that structure and wait for the whole previous pass
+                const PassSlot &pv = pc.slot[(n - 1) % PSLOTS];
+                const unsigned *dep = MODE == MODE_BALANCED ? &pv.done_total : &pv.done[tau >> 8];
+                const unsigned need = MODE == MODE_BALANCED ? NTILES : 256u;
                 unsigned spins = 0;
-                while (ld_acquire(dep) < 256u) {
+                while (ld_acquire(dep) < need) {
                     __nanosleep(32);
                     if ((++spins & 15u) == 0 && n >= (int)ld_relaxed(&pc.stop_pass)) { go = 0; break; }
                 }
@@ -445,14 +487,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persis
         // buffer and stage counter advance by one per resolved pass: pass n sits at a fixed offset from the launch state
         const int cur = (a.cur0 + n) % NBUF;
         fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, nullptr,
-                   sl.s0, sl.minP, &sl.maxP, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, tau, n);
+                   sl.s0, sl.minP, &sl.maxP, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, g0, ncg, FMT, n, tau);
         __syncthreads();                       // every thread's stores and statistics are issued
         TRACE(n, tau, 5);
         if (tid == 0) {
             __threadfence();                   // ... and visible GPU-wide before the tile counts as done
             TRACE(n, tau, 6);
-            atomicAdd(&sl.done[tau % TILE_CLASSES], 1u);
-            if (atomicAdd(&sl.done_total, 1u) == FUSED_TILES - 1) resolve_persist(c, n);
+            if (MODE != MODE_BALANCED) atomicAdd(&sl.done[tau % TILE_CLASSES], 1u);
+            if (atomicAdd(&sl.done_total, 1u) == NTILES - 1) resolve_persist(c, n);
             TRACE(n, tau, 7);
         }
     }
@@ -745,41 +787,45 @@ cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st)
     k_acs_fused<<<FUSED_TILES, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_persist(const PersistArgs &a, bool static_tiles, cudaStream_t st)
+// mode: 0 dynamic queue, 1 static uniform tiles, 2 balanced tiles (needs 148 SMs x 4 CTAs); -1 = best available
+cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    static int checked[64], slots[64];
+    static int checked[64], slots[64], sms_of[64], per_sm_of[64];
     if (dev >= 0 && dev < 64 && !checked[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_acs_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-        if (e != cudaSuccess) return e;
-        // 4 x 33 KiB or 8 x 17 KiB (+1 KiB reserved each) per SM: ask for the large shared-memory carve-out
-        cudaFuncSetAttribute(k_acs_persist<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_acs_persist<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        e = cudaFuncSetAttribute(k_acs_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-        if (e != cudaSuccess) return e;
+        const void *fns[3] = {(const void *)k_acs_persist<MODE_DYNAMIC>, (const void *)k_acs_persist<MODE_STATIC>, (const void *)k_acs_persist<MODE_BALANCED>};
+        for (const void *f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+            if (e != cudaSuccess) return e;
+            // 4 x 33 KiB or 8 x 17 KiB (+1 KiB reserved each) per SM: ask for the large shared-memory carve-out
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist<true>, FUSED_THREADS, sizeof(FusedSmem));
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist<MODE_BALANCED>, FUSED_THREADS, sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        slots[dev] = per_sm * sms;
+        slots[dev] = per_sm * sms; sms_of[dev] = sms; per_sm_of[dev] = per_sm;
         checked[dev] = 1;
     }
+    const bool can_balance = FUSED_TILE_COLS == 64 && sms_of[dev] == BAL_SMS && per_sm_of[dev] == BAL_CTAS_PER_SM;
+    // default: static uniform tiles (measured equal to the dynamic queue and ~5 % faster than the balanced partition,
+    // whose 3-warp tiles still leave 4 warps on three of the four schedulers -- see DESIGN.md)
+    if (mode < 0) mode = slots[dev] >= FUSED_TILES ? MODE_STATIC : MODE_DYNAMIC;
+    if (mode == MODE_BALANCED && !can_balance) mode = MODE_DYNAMIC;
+    if (mode == MODE_STATIC && slots[dev] < FUSED_TILES) mode = MODE_DYNAMIC;
     k_build_optab<<<a.npasses, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.pos0, a.npasses);
     k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful, a.pos0);
-    if (static_tiles) {
-        if (slots[dev] < FUSED_TILES) {
-            fprintf(stderr, "[viterbi224_b200] static tiles need %d co-resident CTAs, the device holds %d\n", FUSED_TILES, slots[dev]);
-            return cudaErrorCooperativeLaunchTooLarge;
-        }
-        PersistArgs args = a;
-        void *params[] = {&args};
-        return cudaLaunchCooperativeKernel((const void *)k_acs_persist<true>, dim3(FUSED_TILES), dim3(FUSED_THREADS), params, sizeof(FusedSmem), st);
-    }
+    PersistArgs args = a;
+    void *params[] = {&args};
+    if (mode == MODE_BALANCED)
+        return cudaLaunchCooperativeKernel((const void *)k_acs_persist<MODE_BALANCED>, dim3(BAL_TILES), dim3(FUSED_THREADS), params, sizeof(FusedSmem), st);
+    if (mode == MODE_STATIC)
+        return cudaLaunchCooperativeKernel((const void *)k_acs_persist<MODE_STATIC>, dim3(FUSED_TILES), dim3(FUSED_THREADS), params, sizeof(FusedSmem), st);
     const long long items = (long long)a.npasses * FUSED_TILES;
     const int grid = (int)(items < slots[dev] ? items : slots[dev]);
-    k_acs_persist<false><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+    k_acs_persist<MODE_DYNAMIC><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)

@@ -51,7 +51,7 @@ struct TraceArgs {
 
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
 cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
-cudaError_t launch_persist(const PersistArgs &a, bool static_tiles, cudaStream_t st);
+cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st);
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

@@ -105,7 +105,7 @@ struct Decoder {
     int *d_flag;
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, static_tiles, chain_seg, chain_warm;
+    int force_single, force_sat, force_careful, per_pass_launch, tile_mode, chain_seg, chain_warm;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     double acs_ms;
@@ -202,7 +202,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
             if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
             PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
                           d->h_ctl->cur, d->h_ctl->T, npasses, d->force_careful};
-            CU(launch_persist(a, d->static_tiles != 0, d->stream));
+            CU(launch_persist(a, d->tile_mode, d->stream));
             p += npasses * FK;
             n += 3;
             passes_in_batch = npasses;
@@ -290,6 +290,7 @@ void *create_viterbi224(int len)
     d->magic = MAGIC;
     d->dev = dev;
     d->len = len;
+    d->tile_mode = -1;
     d->chain_seg = 128;
     d->chain_warm = 256;
     d->ring_bytes = (size_t)len * ROWBYTES;
@@ -646,7 +647,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
-    else if (!strcmp(key, "static_tiles")) d->static_tiles = (int)value;
+    else if (!strcmp(key, "tile_mode")) d->tile_mode = (int)value;      // -1 best, 0 dynamic queue, 1 static, 2 balanced
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

@@ -24,56 +24,66 @@ static void emu_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *opta
     if (mn < minP[T]) minP[T] = mn;
 }
 
+struct EmuTile { uint32_t g0, ncg; };
+
 extern "C" {
 
 // One fused pass: oldP/newP 2^23 uint16, rows = 8 decision rows in fused layout, syms = 16 bytes.
+// balanced = 0: uniform tiles of FUSED_COLGROUPS column groups; 1: the 592-tile balanced partition.
 // stats: s0[1..8], minP[1..8], maxP_end written to out_stats[0..8], [9..17], [18].
-void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const uint8_t *syms, int sub, uint32_t *out_stats)
+void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const uint8_t *syms, int sub, uint32_t *out_stats, int balanced)
 {
-    std::vector<uint32_t> optab(OPTAB_WORDS);
+    alignas(16) static uint32_t optab[OPTAB_WORDS];
     for (int e = 0; e < OPTAB_WORDS; e++) optab[e] = optab_entry(e, syms);
     uint32_t s0[FK + 1] = {0}, minP[FK + 1];
     for (int t = 0; t <= FK; t++) minP[t] = 0xffffffffu;
     uint32_t maxP = 0;
     const uint32_t sub2 = (uint32_t)sub * 0x10001u;
-    std::vector<uint32_t> tile(256 * FUSED_TILE_COLS / 2);
-    for (uint32_t tau = 0; tau < FUSED_TILES; tau++) {
+    std::vector<EmuTile> tiles;
+    if (balanced) {
+        for (uint32_t rank = 0; rank < BAL_SMS; rank++)
+            for (uint32_t slot = 0; slot < BAL_CTAS_PER_SM; slot++) { EmuTile t; balanced_tile(rank, slot, t.g0, t.ncg); tiles.push_back(t); }
+    } else {
+        for (uint32_t t = 0; t < FUSED_TILES; t++) tiles.push_back({t * FUSED_COLGROUPS, (uint32_t)FUSED_COLGROUPS});
+    }
+    std::vector<uint32_t> tile(256 * 8 * 4);
+    for (const EmuTile &tl : tiles) {
+        const uint32_t g0 = tl.g0, ncg = tl.ncg, nthreads = 16 * ncg;
         // round 1
-        for (uint32_t tid = 0; tid < FUSED_THREADS; tid++) {
-            const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS, chunk = tau * FUSED_THREADS + tid;
+        for (uint32_t tid = 0; tid < nthreads; tid++) {
+            const uint32_t thr = tid / ncg, g = tid % ncg, G = g0 + g, chunk = g0 * 16 + tid;
             uint32_t A[16][4];
             for (int mh = 0; mh < 16; mh++) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(oldP + ((size_t)(mh * 16 + thr) * 32768 + tau * FUSED_TILE_COLS + g * 8));
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(oldP + ((size_t)(mh * 16 + thr) * 32768 + G * 8));
                 for (int q = 0; q < 4; q++) A[mh][q] = src[q] - sub2;
             }
-            const uint32_t pbase = (thr << 15) | (tau << FUSED_COLS_LOG2) | (g << 3);
-            const bool first = tau == 0 && tid == 0;
-            emu_stage<1>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<2>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<3>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<4>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
+            const uint32_t pbase = (thr << 15) | (G << 3);
+            const bool first = G == 0 && thr == 0;
+            emu_stage<1>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<2>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<3>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<4>(A, pbase, optab, rows, chunk, s0, minP, first);
             for (int mh = 0; mh < 16; mh++)
-                for (int q = 0; q < 4; q++) tile[((mh * 16 + thr) * FUSED_COLGROUPS + g) * 4 + q] = A[mh][q];
+                for (int q = 0; q < 4; q++) tile[((mh * 16 + thr) * ncg + g) * 4 + q] = A[mh][q];
         }
         // round 2
-        for (uint32_t tid = 0; tid < FUSED_THREADS; tid++) {
-            const uint32_t thr = tid / FUSED_COLGROUPS, g = tid % FUSED_COLGROUPS, chunk = tau * FUSED_THREADS + tid;
+        for (uint32_t tid = 0; tid < nthreads; tid++) {
+            const uint32_t thr = tid / ncg, g = tid % ncg, G = g0 + g, chunk = g0 * 16 + tid;
             uint32_t A[16][4];
             for (int ml = 0; ml < 16; ml++)
-                for (int q = 0; q < 4; q++) A[ml][q] = tile[((thr * 16 + ml) * FUSED_COLGROUPS + g) * 4 + q];
-            const uint32_t pbase = (thr << 19) | (tau << FUSED_COLS_LOG2) | (g << 3);
-            const bool first = tau == 0 && tid == 0;
-            emu_stage<5>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<6>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<7>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
-            emu_stage<8>(A, pbase, optab.data(), rows, chunk, s0, minP, first);
+                for (int q = 0; q < 4; q++) A[ml][q] = tile[((thr * 16 + ml) * ncg + g) * 4 + q];
+            const uint32_t pbase = (thr << 19) | (G << 3);
+            const bool first = G == 0 && thr == 0;
+            emu_stage<5>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<6>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<7>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<8>(A, pbase, optab, rows, chunk, s0, minP, first);
             uint32_t mx = tile_max(A);
             if (mx > maxP) maxP = mx;
-            const uint32_t jbase = tau * FUSED_TILE_COLS + g * 8;
             for (int q = 0; q < 4; q++)
                 for (int h = 0; h < 2; h++)
                     for (int ml = 0; ml < 16; ml++)
-                        newP[((size_t)(jbase + q * 2 + h) << 8) + thr * 16 + ml] = (uint16_t)(A[ml][q] >> (16 * h));
+                        newP[((size_t)(G * 8 + q * 2 + h) << 8) + thr * 16 + ml] = (uint16_t)(A[ml][q] >> (16 * h));
         }
     }
     for (int t = 0; t <= FK; t++) { out_stats[t] = s0[t]; out_stats[FK + 1 + t] = minP[t]; }
@@ -81,11 +91,11 @@ void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const 
 }
 
 // fused-layout row written by stage t -> canonical (reference) layout
-void emu_canon_row(int t, const uint32_t *fused_row, uint32_t *canon_row)
+void emu_canon_row(int fmt, const uint32_t *fused_row, uint32_t *canon_row)
 {
     memset(canon_row, 0, ROWBYTES);
     for (uint32_t s = 0; s < NSTATES; s++) {
-        const uint32_t a = fused_bit_address(t, s);
+        const uint32_t a = fused_bit_address(fmt, s);
         canon_row[s >> 5] |= ((fused_row[a >> 5] >> (a & 31)) & 1u) << (s & 31);
     }
 }

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import isee3_decoder_b200 as v224
 n = 16384
 bits, syms = v224.streams.telemetry_stream(n, 3.0, seed=5)
-for name, opts in [("dynamic queue", {}), ("static coop", {"static_tiles": 1}), ("per-pass launch", {"per_pass_launch": 1}), ("single-stage", {"force_single": 1})]:
+for name, opts in [("balanced", {"tile_mode": 2}), ("dynamic queue", {"tile_mode": 0}), ("static coop", {"tile_mode": 1}), ("per-pass launch", {"per_pass_launch": 1}), ("single-stage", {"force_single": 1})]:
     with v224.Viterbi224(n) as d:
         for k, v in opts.items():
             d.set_option(k, v)

@@ -11,7 +11,7 @@ n = 64 * 8
 bits, syms = v224.streams.telemetry_stream(n, 3.0, seed=5)
 static = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 with v224.Viterbi224(n) as d:
-    d.set_option("static_tiles", static)
+    d.set_option("tile_mode", static)
     d.init(0); d.update_blk(syms, n)
     d.init(0); d.update_blk(syms, n)
     tr = np.zeros(64 * 1024 * 8, dtype=np.uint64)
