@@ -3,6 +3,7 @@
 // Code parameters follow the reference's active code block (code.h:54-63, MCQLI-24).
 #pragma once
 #include <cstdint>
+#include <cstddef>
 #include <cuda_runtime.h>
 
 namespace v224 {
@@ -64,11 +65,38 @@ constexpr uint8_t ROWFMT_CANON = 0;
 // R = P + O for the 64-bit offset O below.  Decisions depend on metric differences only, so
 // any O is exact as long as neither side saturates; the resolver tracks the reference's
 // renormalisation test (viterbi224_sse2.c:351-377) on R virtually and keeps P small.
+// Per-pass statistics.  Same-address atomics serialise in L2 at a few ns each, and a pass issues thousands of
+// them, so minima / maxima are spread over STAT_BUCKETS buckets, each in its own 32-byte sector.
+constexpr int STAT_BUCKETS = 16;
+struct PassStats {
+    unsigned s0[FK + 1];                        // P of state 0 after stage t
+    unsigned minP[FK + 1][STAT_BUCKETS][8];     // min of P after stage t ([FK] always, the others in careful passes); [..][0] used
+    unsigned maxP[STAT_BUCKETS][8];             // max of P after the last stage; [..][0] used
+};
+__host__ __device__ inline void stats_reset(PassStats &s)
+{
+    for (int t = 0; t <= FK; t++) {
+        s.s0[t] = 0;
+        for (int b = 0; b < STAT_BUCKETS; b++) s.minP[t][b][0] = 0xffffffffu;
+    }
+    for (int b = 0; b < STAT_BUCKETS; b++) s.maxP[b][0] = 0;
+}
+__host__ __device__ inline unsigned stats_min(const PassStats &s, int t)
+{
+    unsigned m = 0xffffffffu;
+    for (int b = 0; b < STAT_BUCKETS; b++) { const unsigned v = *(volatile const unsigned *)&s.minP[t][b][0]; m = v < m ? v : m; }
+    return m;
+}
+__host__ __device__ inline unsigned stats_max(const PassStats &s)
+{
+    unsigned m = 0;
+    for (int b = 0; b < STAT_BUCKETS; b++) { const unsigned v = *(volatile const unsigned *)&s.maxP[b][0]; m = v > m ? v : m; }
+    return m;
+}
+
 // Bookkeeping of one in-flight pass of the persistent kernel.
 struct PassSlot {
-    unsigned s0[FK + 1];    // P of state 0 after stage t
-    unsigned minP[FK + 1];  // global min of P after stage t ([FK] always, the others in careful passes)
-    unsigned maxP;          // global max of P after the last stage
+    PassStats st;
     unsigned done[TILE_CLASSES];   // finished tiles by (tile index mod TILE_CLASSES): what the next pass waits on
     unsigned done_total;
     int sub;                // what this pass subtracts from every P while loading
@@ -102,14 +130,13 @@ struct Ctl {
     long long spread;       // max - min after the last stage (packed-arithmetic range watch)
     int  error;             // sticky: internal invariant violated
     unsigned ticket;        // CTA completion counter of the running pass
-    // per-pass statistics, reset by the resolver
-    unsigned s0[FK + 1];    // P of state 0 after stage t (t = 1..k)
-    unsigned minP[FK + 1];  // global min of P after stage t (careful passes; [k] always)
-    unsigned maxP_end;      // global max of P after the last stage
     // counters for tests / bench
     unsigned n_fused, n_single, n_careful, n_sat, n_invalidated;
+    // ---- everything above is what the host mirrors after each call (CTL_HOST_BYTES) ----
+    PassStats st;           // statistics of the running per-pass / single-stage kernel, reset by its resolver
     PersistCtl pc;
 };
+constexpr size_t CTL_HOST_BYTES = offsetof(Ctl, st);
 
 // ---- tile partitions of the 4096 column groups (8 columns each) -------------------------------
 // UNIFORM: tile t = groups [t*CG, (t+1)*CG), CG = FUSED_COLGROUPS.

@@ -51,8 +51,7 @@ __device__ __forceinline__ void st_v8(void *p, const uint32_t (&v)[8])   // 256-
 __device__ __forceinline__ void reset_stats(Ctl *c)
 {
 #pragma unroll
-    for (int t = 0; t <= FK; t++) { c->s0[t] = 0; c->minP[t] = 0xffffffffu; }
-    c->maxP_end = 0;
+    stats_reset(c->st);
     c->ticket = 0;
 }
 
@@ -63,10 +62,11 @@ __device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
 {
     long long O = sat ? -32768ll : c->O;      // a SAT stage stores P = R + 32768
     for (int t = 1; t <= ks; t++) {
-        const long long R0 = (long long)c->s0[t] + O;
+        const long long R0 = (long long)*(volatile unsigned *)&c->st.s0[t] + O;
         if (R0 >= RENORM_TRIGGER) {                                   // :351 state 0 only
-            if (!(careful || t == ks) || c->minP[t] == 0xffffffffu) { c->error |= 1; break; }
-            const long long minR = (long long)c->minP[t] + O;         // :358-366 global minimum
+            const unsigned mnt = stats_min(c->st, t);
+            if (!(careful || t == ks) || mnt == 0xffffffffu) { c->error |= 1; break; }
+            const long long minR = (long long)mnt + O;                // :358-366 global minimum
             // :354,:366 the minimum is read through a uint16_t: a negative one counts 65536 more
             const long long adjust = (minR < 0 ? minR + 65536 : minR) + 32768;
             c->renormals += adjust;                                   // :367
@@ -74,7 +74,7 @@ __device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
             O -= minR + 32768;                                        // :373 (mod 2^16 == this, min -> SHRT_MIN)
         }
     }
-    const unsigned mn = c->minP[ks], mx = c->maxP_end, z = c->s0[ks];
+    const unsigned mn = stats_min(c->st, ks), mx = stats_max(c->st), z = *(volatile unsigned *)&c->st.s0[ks];
     if (mn == 0xffffffffu || mx < mn) c->error |= 2;
     O += mn;                         // the next pass subtracts mn from every P while loading
     c->sub = (int)mn;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_build_optab(uint32_t *optab, const uint
 
 template <int T>
 __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t *ring, uint8_t *row_fmt,
-                                            int len, unsigned *s0, unsigned *minP, long long T0, bool careful, bool first, uint32_t chunk,
+                                            int len, PassStats &st, long long T0, bool careful, bool first, uint32_t chunk,
                                             int fmt_base)
 {
     uint32_t dw[4];
@@ -141,12 +141,12 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase
     const long long row = (T0 + T - 1) % len;
     st_cs_v4(reinterpret_cast<uint8_t *>(ring) + (size_t)row * ROWBYTES + (size_t)chunk * 16, make_uint4(dw[0], dw[1], dw[2], dw[3]));
     if (first) {
-        s0[T] = A[0][0] & 0xffffu;               // slot 0 always holds state 0
+        st.s0[T] = A[0][0] & 0xffffu;            // slot 0 always holds state 0
         row_fmt[row] = (uint8_t)(fmt_base + T);
     }
     if (careful && T < FK) {
         uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
-        if ((threadIdx.x & 31) == 0) atomicMin(&minP[T], mn);
+        if ((threadIdx.x & 31) == 0) atomicMin(&st.minP[T][(blockIdx.x * 4 + (threadIdx.x >> 5)) % STAT_BUCKETS][0], mn);
     }
 }
 
@@ -156,7 +156,7 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][4], uint32_t pbase
 // the CTA barriers company (a 6-group tile leaves its fourth warp idle).
 // LDCG: metrics are read through L2 only (another SM wrote them, possibly within this launch).
 __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, uint16_t *newm, uint32_t *ring, uint8_t *row_fmt, int len,
-                                           const uint32_t *optab_g, unsigned *s0, unsigned *minP, unsigned *maxP, long long T0, uint32_t sub,
+                                           const uint32_t *optab_g, PassStats &st, long long T0, uint32_t sub,
                                            bool careful, uint32_t g0, uint32_t ncg, int fmt_base, int trace_n = 1 << 30, uint32_t trace_id = 0)
 {
     const uint32_t tid = threadIdx.x;
@@ -189,10 +189,10 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
 #endif
     if (active) {
         const uint32_t pbase = (thr << 15) | (G << 3);
-        fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<1>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<2>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<3>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<4>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
         // ---- exchange: rows m = mh*16 + ml; element (row, g) at 16-byte index row*ncg + g.  A quarter-warp
         // touches 8 consecutive 16-byte slots when ncg = 8 (conflict-free); ncg = 6 costs a few 2-way conflicts ----
 #pragma unroll
@@ -210,10 +210,10 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
 #endif
         // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
         const uint32_t pbase = (thr << 19) | (G << 3);
-        fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
-        fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, s0, minP, T0, careful, first, chunk, fmt_base);
+        fused_stage<5>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<6>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<7>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
+        fused_stage<8>(A, pbase, sm.optab, ring, row_fmt, len, st, T0, careful, first, chunk, fmt_base);
 #ifdef V224_TRACE
         if (tid == 0 && trace_n < 64) g_trace[(trace_n * 1024 + trace_id) * 8 + 4] = gtime();
 #endif
@@ -221,7 +221,11 @@ __device__ __forceinline__ void fused_tile(FusedSmem &sm, const uint16_t *oldm, 
         {
             const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
             const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
-            if ((tid & 31) == 0) { atomicMin(&minP[FK], mn); atomicMax(maxP, mx); }
+            if ((tid & 31) == 0) {
+                const uint32_t b = (blockIdx.x * 4 + (tid >> 5)) % STAT_BUCKETS;
+                atomicMin(&st.minP[FK][b][0], mn);
+                atomicMax(&st.maxP[b][0], mx);
+            }
         }
         // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B ----
         {
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_fused(
     if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
     const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.optab,
-               c->s0, c->minP, &c->maxP_end, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x * FUSED_COLGROUPS, FUSED_COLGROUPS, 0);
+               c->st, c->T, (uint32_t)c->sub * 0x10001u, careful, blockIdx.x * FUSED_COLGROUPS, FUSED_COLGROUPS, 0);
 
     // ---- last CTA resolves the pass ----
     __shared__ unsigned s_ticket;
@@ -291,8 +295,7 @@ __device__ __forceinline__ void st_release(unsigned *p, unsigned v)
 __device__ __forceinline__ void slot_reset(PassSlot &s)
 {
 #pragma unroll
-    for (int t = 0; t <= FK; t++) { s.s0[t] = 0; s.minP[t] = 0xffffffffu; }
-    s.maxP = 0;
+    stats_reset(s.st);
     for (int k = 0; k < TILE_CLASSES; k++) s.done[k] = 0;
     s.done_total = 0;
 }
@@ -339,17 +342,18 @@ __device__ void resolve_persist(Ctl *c, int n)
         // the adds of stage t clip in the reference iff some R + branch metric exceeds SHRT_MAX (:296-299)
         if (maxR + 510 > 32767) { valid = false; break; }
         maxR += 510;
-        const long long R0 = (long long)sl.s0[t] + O;
+        const long long R0 = (long long)*(volatile unsigned *)&sl.st.s0[t] + O;
         if (R0 >= RENORM_TRIGGER) {                                        // viterbi224_sse2.c:351
-            if (!(careful || t == FK) || sl.minP[t] == 0xffffffffu) { c->error |= 1; valid = false; break; }
-            const long long minR = (long long)sl.minP[t] + O;             // :358-366
+            const unsigned mnt = stats_min(sl.st, t);
+            if (!(careful || t == FK) || mnt == 0xffffffffu) { c->error |= 1; valid = false; break; }
+            const long long minR = (long long)mnt + O;                    // :358-366
             renormals += (minR < 0 ? minR + 65536 : minR) + 32768;        // :354,:366,:367 (uint16 read of the minimum)
             count++;
             O -= minR + 32768;                                             // :373
             maxR -= minR + 32768;
         }
     }
-    const unsigned mn = sl.minP[FK], mx = sl.maxP, z = sl.s0[FK];
+    const unsigned mn = stats_min(sl.st, FK), mx = stats_max(sl.st), z = *(volatile unsigned *)&sl.st.s0[FK];
     if (valid && (mn == 0xffffffffu || mx < mn)) { c->error |= 2; valid = false; }
     if (valid && (long long)mx - mn > MAX_FAST_SPREAD) valid = false;
     if (valid) {
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persis
         // buffer and stage counter advance by one per resolved pass: pass n sits at a fixed offset from the launch state
         const int cur = (a.cur0 + n) % NBUF;
         fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, nullptr,
-                   sl.s0, sl.minP, &sl.maxP, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, g0, ncg, FMT, n, tau);
+                   sl.st, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, g0, ncg, FMT, n, tau);
         __syncthreads();                       // every thread's stores and statistics are issued
         TRACE(n, tau, 5);
         if (tid == 0) {
@@ -564,13 +568,20 @@ __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
 
     const uint32_t wmn = __reduce_min_sync(0xffffffffu, (uint32_t)mn);
     const uint32_t wmx = __reduce_max_sync(0xffffffffu, (uint32_t)mx);
-    if ((threadIdx.x & 31) == 0) { atomicMin(&c->minP[1], wmn); atomicMax(&c->maxP_end, wmx); }
-    if (gid == 0) { c->s0[1] = out[0] & 0xffffu; a.row_fmt[row] = ROWFMT_CANON; }
+    __shared__ uint32_t s_mn[8], s_mx[8];
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = wmn; s_mx[threadIdx.x >> 5] = wmx; }
+    if (gid == 0) { c->st.s0[1] = out[0] & 0xffffu; a.row_fmt[row] = ROWFMT_CANON; }
 
     __shared__ unsigned s_ticket;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&c->ticket, 1u);
+    if (threadIdx.x == 0) {
+        uint32_t bmn = s_mn[0], bmx = s_mx[0];
+        for (int w = 1; w < 8; w++) { bmn = min(bmn, s_mn[w]); bmx = max(bmx, s_mx[w]); }
+        atomicMin(&c->st.minP[1][blockIdx.x % STAT_BUCKETS][0], bmn);
+        atomicMax(&c->st.maxP[blockIdx.x % STAT_BUCKETS][0], bmx);
+        __threadfence();
+        s_ticket = atomicAdd(&c->ticket, 1u);
+    }
     __syncthreads();
     if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) {
         __threadfence();
@@ -810,9 +821,10 @@ cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st)
         checked[dev] = 1;
     }
     const bool can_balance = FUSED_TILE_COLS == 64 && sms_of[dev] == BAL_SMS && per_sm_of[dev] == BAL_CTAS_PER_SM;
-    // default: static uniform tiles (measured equal to the dynamic queue and ~5 % faster than the balanced partition,
-    // whose 3-warp tiles still leave 4 warps on three of the four schedulers -- see DESIGN.md)
-    if (mode < 0) mode = slots[dev] >= FUSED_TILES ? MODE_STATIC : MODE_DYNAMIC;
+    // default: the dynamic queue -- measured 16.5 us per pass against 20.6 (static) and 20.3 (balanced) on B200
+    // (tools/ab_kernels.py, profiles/); the balanced partition's 3-warp tiles still leave 4 warps on three of
+    // the four schedulers, and cooperative launches place CTAs less evenly than the queue does.
+    if (mode < 0) mode = MODE_DYNAMIC;
     if (mode == MODE_BALANCED && !can_balance) mode = MODE_DYNAMIC;
     if (mode == MODE_STATIC && slots[dev] < FUSED_TILES) mode = MODE_DYNAMIC;
     k_build_optab<<<a.npasses, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.pos0, a.npasses);

@@ -140,7 +140,7 @@ int grow(void **buf, size_t *cap, size_t need)
 
 int sync_ctl(Decoder *d)
 {
-    CU(cudaMemcpyAsync(d->h_ctl, d->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaMemcpyAsync(d->h_ctl, d->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
     if (d->h_ctl->error) { set_err("device control block reports invariant violation %d", d->h_ctl->error); return -1; }
     return 0;
