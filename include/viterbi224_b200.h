@@ -41,6 +41,11 @@ int v224x_stream_decode_dev(void *p, const unsigned char *dev_syms, int nbits, i
 /* update_viterbi224_blk with the symbols already in device memory. */
 int v224x_update_dev(void *p, const unsigned char *dev_syms, int nbits);
 
+/* Advance nctx (1..4) independent decoders of one GPU by nbits stages each, in lockstep: one persistent launch
+ * works through all of them, so the GPU does not idle at any decoder's pass boundary.  Each decoder ends in exactly
+ * the state nctx separate v224x_update_dev() calls would leave.  renorms_out[i] (optional) = decoder i's return value. */
+int v224x_update_multi_dev(void **handles, const unsigned char *const *dev_syms, int nctx, int nbits, int *renorms_out);
+
 /* init variant for time-segmented decoding: every metric = SHRT_MIN + bias and no state is
  * favoured (start_state < 0), or init_viterbi224 semantics (start_state >= 0). */
 int v224x_init_uniform(void *p, int bias, int start_state);

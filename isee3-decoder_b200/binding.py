@@ -14,7 +14,7 @@ ABI_SYMBOLS = ["create_viterbi224", "init_viterbi224", "update_viterbi224_blk", 
                "decodebit_viterbi224", "decodeword_viterbi224", "max_metric_viterbi224", "min_metric_viterbi224",
                "delete_viterbi224"]
 EXT_SYMBOLS = ["v224x_device_count", "v224x_set_device", "v224x_last_error", "v224x_version", "v224x_stream_decode",
-               "v224x_stream_decode_dev", "v224x_update_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
+               "v224x_stream_decode_dev", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
                "v224x_h2d", "v224x_d2h", "v224x_host_alloc_pinned", "v224x_host_free_pinned", "v224x_timer_start",
                "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms", "v224x_kernel_time_passes",
                "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option"]
@@ -65,6 +65,7 @@ def load_library():
         "v224x_stream_decode": (ci, [vp, vp, ci, ci, vp]),
         "v224x_stream_decode_dev": (ci, [vp, vp, ci, ci, vp]),
         "v224x_update_dev": (ci, [vp, vp, ci]),
+        "v224x_update_multi_dev": (ci, [vp, vp, ci, ci, vp]),
         "v224x_init_uniform": (ci, [vp, ci, ci]),
         "v224x_dev_alloc": (vp, [vp, ctypes.c_size_t]),
         "v224x_dev_free": (None, [vp, vp]),
@@ -199,6 +200,19 @@ class Viterbi224:
 
     def update_dev(self, dev_syms, nbits):
         return self._check(self.lib.v224x_update_dev(self.h, dev_syms, int(nbits)), "v224x_update_dev")
+
+    @staticmethod
+    def update_multi_dev(decoders, dev_syms, nbits):
+        """Advance several decoders of one GPU in lockstep (v224x_update_multi_dev).  Returns per-decoder renorm counts."""
+        lib = load_library()
+        n = len(decoders)
+        hs = (ctypes.c_void_p * n)(*[d.h for d in decoders])
+        ps = (ctypes.c_void_p * n)(*dev_syms)
+        ren = (ctypes.c_int * n)()
+        rc = lib.v224x_update_multi_dev(hs, ps, n, int(nbits), ren)
+        if rc < 0:
+            raise V224Error("v224x_update_multi_dev failed: " + (lib.v224x_last_error() or b"").decode())
+        return list(ren)
 
     def stream_decode_dev(self, dev_syms, nbits, delay, dev_bits):
         return self._check(self.lib.v224x_stream_decode_dev(self.h, dev_syms, int(nbits), int(delay), dev_bits), "v224x_stream_decode_dev")

@@ -121,8 +121,8 @@ struct Ctl {
     long long O;            // R = P + O
     long long renormals;    // the reference's running `renormals` (viterbi224_sse2.c:33,367)
     long long T;            // trellis stages since init (ring position = T % len)
-    int  pos;               // stages completed within the current update call
-    int  renorm_count;      // renormalisations within the current update call (return value)
+    int  renorm_count;      // renormalisations since the last init (update returns the difference over the call)
+    int  pad0;
     int  sub;               // amount the next pass subtracts from every P while loading
     int  cur;               // which metric buffer is the "old" one
     long long R0;           // reference metric of state 0 after the last stage (renorm trigger watch)

@@ -83,7 +83,6 @@ __device__ void resolve_pass(Ctl *c, int ks, bool careful, bool sat)
     c->maxR = (long long)mx - mn + O;
     c->spread = (long long)mx - mn;
     c->T += ks;
-    c->pos += ks;
     c->cur = (c->cur + 1) % NBUF;
     reset_stats(c);
 }
@@ -104,7 +103,6 @@ __global__ void __launch_bounds__(256) k_init(uint16_t *m0, Ctl *c, uint32_t sta
         c->O = -32768;
         c->renormals = 0;
         c->T = 0;
-        c->pos = 0;
         c->renorm_count = 0;
         c->sub = 0;
         c->R0 = (start_state == 0 && start_value >= 0 ? start_value : bias) - 32768;
@@ -251,7 +249,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_fused(
     Ctl *c = a.ctl;
 
     // Every CTA takes the same go / no-go decision from the (quiescent) control block.
-    if (c->pos != a.expected_pos || c->error) return;
+    if (c->T != a.expected_T || c->error) return;
     if (c->maxR + 510ll * FK > 32767 || c->spread > MAX_FAST_SPREAD) return;   // reference could saturate: host runs SAT stages
     const bool careful = a.force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     fused_tile(sm, a.metrics[c->cur], a.metrics[(c->cur + 1) % NBUF], a.ring, a.row_fmt, a.len, a.optab,
@@ -300,7 +298,7 @@ __device__ __forceinline__ void slot_reset(PassSlot &s)
     s.done_total = 0;
 }
 
-__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, int expected_pos)
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T)
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
@@ -317,7 +315,7 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, int expe
     pc.slot[0].careful = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     pc.slot[1].careful = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
     int stop = npasses;
-    if (c->spread > MAX_FAST_SPREAD || c->error || c->pos != expected_pos) stop = 0;
+    if (c->spread > MAX_FAST_SPREAD || c->error || c->T != expected_T) stop = 0;
     // non-careful passes are not validated stage by stage: keep them well away from saturation
     if (!pc.slot[0].careful && c->maxR + 510ll * FK > 32767) stop = 0;
     if (stop > 1 && !pc.slot[1].careful && c->maxR + 510ll * 2 * FK > 32767) stop = 1;
@@ -368,7 +366,6 @@ __device__ void resolve_persist(Ctl *c, int n)
         c->maxR = (long long)mx + O;
         c->spread = (long long)mx - mn;
         c->T += FK;
-        c->pos += FK;
         c->cur = (c->cur + 1) % NBUF;
         c->n_fused++;
         if (careful) c->n_careful++;
@@ -504,6 +501,61 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persis
     }
 }
 
+// Multi-context variant of the dynamic queue: item = (pass n, context s, tile), pass-major, contexts in turn.
+// Every context keeps its own control block, buffers and resolver; only the queue head (context 0's) is shared.
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_CTAS_PER_SM) k_acs_persist_multi(MultiArgs m)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    __shared__ int s_go, s_sub, s_careful;
+    __shared__ unsigned s_item;
+    const uint32_t tid = threadIdx.x;
+    unsigned *queue = &m.ctx[0].ctl->pc.next_item;
+    const unsigned per_pass = (unsigned)m.nctx * FUSED_TILES;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(queue, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        const int n = (int)(item / per_pass);
+        if (n >= m.npasses) break;
+        const unsigned r = item % per_pass, s = r / FUSED_TILES, w = r % FUSED_TILES;
+        const uint32_t tau = (w % 256u) * TILE_CLASSES + w / 256u;             // a pass emits its tile classes in turn
+        const PersistArgs &a = m.ctx[s];
+        Ctl *c = a.ctl;
+        PersistCtl &pc = c->pc;
+        PassSlot &sl = pc.slot[n % PSLOTS];
+        for (int e = tid; e < OPTAB_WORDS / 4; e += FUSED_THREADS)
+            reinterpret_cast<uint4 *>(sm.optab)[e] = __ldcg(reinterpret_cast<const uint4 *>(a.optab + (size_t)n * OPTAB_WORDS) + e);
+        if (tid == 0) {
+            while ((int)ld_relaxed(&pc.resolved_upto) < n - 1) __nanosleep(200);      // parameters of pass n exist
+            s_sub = (int)ld_relaxed(&sl.sub);
+            s_careful = (int)ld_relaxed(&sl.careful);
+            int go = n < (int)ld_relaxed(&pc.stop_pass);
+            if (go && n > 0) {
+                const unsigned *dep = &pc.slot[(n - 1) % PSLOTS].done[tau >> 8];
+                unsigned spins = 0;
+                while (ld_acquire(dep) < 256u) {
+                    __nanosleep(32);
+                    if ((++spins & 15u) == 0 && n >= (int)ld_relaxed(&pc.stop_pass)) { go = 0; break; }
+                }
+            }
+            s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) continue;                   // this context stopped (saturation watch); the others go on
+        const int cur = (a.cur0 + n) % NBUF;
+        fused_tile(sm, a.metrics[cur], a.metrics[(cur + 1) % NBUF], a.ring, a.row_fmt, a.len, nullptr,
+                   sl.st, a.T0 + (long long)n * FK, (uint32_t)s_sub * 0x10001u, s_careful != 0, tau * FUSED_COLGROUPS, FUSED_COLGROUPS, 0);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&sl.done[tau % TILE_CLASSES], 1u);
+            if (atomicAdd(&sl.done_total, 1u) == FUSED_TILES - 1) resolve_persist(c, n);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // single stage (remainders, per-bit streaming, exact saturating fallback)
 // ------------------------------------------------------------------------------------------
@@ -512,7 +564,7 @@ template <bool SAT>
 __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
 {
     Ctl *c = a.ctl;
-    if (c->pos != a.expected_pos || c->error) return;
+    if (c->T != a.expected_T || c->error) return;
     if (!SAT && (c->maxR + 510 > 32767 || c->spread > MAX_FAST_SPREAD)) return;   // reference could saturate: use the SAT variant
     const long long T0 = c->T;
     const int sub = c->sub;
@@ -828,7 +880,7 @@ cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st)
     if (mode == MODE_BALANCED && !can_balance) mode = MODE_DYNAMIC;
     if (mode == MODE_STATIC && slots[dev] < FUSED_TILES) mode = MODE_DYNAMIC;
     k_build_optab<<<a.npasses, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.pos0, a.npasses);
-    k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful, a.pos0);
+    k_persist_begin<<<1, 1, 0, st>>>(a.ctl, a.npasses, a.force_careful, a.T0);
     PersistArgs args = a;
     void *params[] = {&args};
     if (mode == MODE_BALANCED)
@@ -838,6 +890,33 @@ cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st)
     const long long items = (long long)a.npasses * FUSED_TILES;
     const int grid = (int)(items < slots[dev] ? items : slots[dev]);
     k_acs_persist<MODE_DYNAMIC><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_persist_multi(const MultiArgs &m, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int checked[64], slots[64];
+    if (dev >= 0 && dev < 64 && !checked[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_acs_persist_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(k_acs_persist_multi, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist_multi, FUSED_THREADS, sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        slots[dev] = per_sm * sms;
+        checked[dev] = 1;
+    }
+    for (int s = 0; s < m.nctx; s++) {
+        const PersistArgs &a = m.ctx[s];
+        k_build_optab<<<m.npasses, OPTAB_WORDS, 0, st>>>(a.optab, a.syms + 2 * (size_t)a.pos0, m.npasses);
+        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0);
+    }
+    const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
+    const int grid = (int)(items < slots[dev] ? items : slots[dev]);
+    k_acs_persist_multi<<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(m);
     return cudaGetLastError();
 }
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)

@@ -12,7 +12,8 @@ struct FusedArgs {
     const uint8_t *syms;     // device symbols of the running update call (2 per bit)
     uint32_t *optab;         // scratch: this pass's operand table (256 words)
     int len;                 // ring rows
-    int expected_pos;        // stages of this call that must already be done
+    int expected_pos;        // index of this pass's first symbol pair in syms
+    long long expected_T;    // the control block's stage counter this launch was issued for (else it declines)
     int force_careful;       // test knob: record per-stage minima regardless
 };
 
@@ -31,6 +32,15 @@ struct PersistArgs {
     int force_careful;
 };
 
+// Several independent decoders advanced in lockstep by ONE persistent launch (dynamic queue only): while the tiles
+// of one decoder's pass drain, the CTAs already work on the next decoder's pass, so nobody waits at a pass boundary.
+constexpr int MAX_CTX = 4;
+struct MultiArgs {
+    int nctx;
+    int npasses;             // per context
+    PersistArgs ctx[MAX_CTX];
+};
+
 struct SingleArgs {
     Ctl *ctl;
     uint16_t *metrics[NBUF];
@@ -38,7 +48,8 @@ struct SingleArgs {
     uint8_t *row_fmt;
     const uint8_t *syms;
     int len;
-    int expected_pos;
+    int expected_pos;        // index of this stage's symbol pair in syms
+    long long expected_T;    // the control block's stage counter this launch was issued for (else it declines)
     int use_arg_syms;        // per-bit streaming: the two symbols travel as kernel arguments
     int sym0, sym1;
 };
@@ -52,6 +63,7 @@ struct TraceArgs {
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
 cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
 cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st);
+cudaError_t launch_persist_multi(const MultiArgs &m, cudaStream_t st);
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

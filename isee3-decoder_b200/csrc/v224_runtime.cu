@@ -182,11 +182,14 @@ int do_init(Decoder *d, int bias, int start_state)
 TraceArgs trace_args(Decoder *d) { return TraceArgs{d->ring, d->row_fmt, d->len}; }
 
 // Run nbits trellis stages on device-resident symbols.  Returns renormalisation count or -1.
+// Every launch carries the stage counter it was issued for; a kernel whose predecessor declined (saturation
+// watch) finds a different counter in the control block and declines too, so the host can enqueue a whole
+// batch without looking and sort it out afterwards.
 int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1, int arg_s1 = -1)
 {
     if (nbits <= 0) return 0;
-    // pos / renorm_count live in the control block; zero them for this call
-    CU(cudaMemsetAsync(&d->ctl->pos, 0, 2 * sizeof(int), d->stream));   // pos and renorm_count are adjacent
+    const long long T_start = d->h_ctl->T;
+    const int ren_start = d->h_ctl->renorm_count;
     constexpr int BATCH_STAGES = 8192;
     int pos = 0;
     while (pos < nbits) {
@@ -201,7 +204,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
             const int npasses = (end - p) / FK;
             if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
             PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
-                          d->h_ctl->cur, d->h_ctl->T, npasses, d->force_careful};
+                          d->h_ctl->cur, T_start + p, npasses, d->force_careful};
             CU(launch_persist(a, d->tile_mode, d->stream));
             p += npasses * FK;
             n += 3;
@@ -210,13 +213,15 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         while (p < end) {
             if (fuse && d->per_pass_launch && end - p >= FK) {
                 if (grow((void **)&d->optab, &d->optab_cap, 1024)) return -1;
-                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p, d->force_careful};
+                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p, T_start + p,
+                            d->force_careful};
                 CU(launch_fused(a, d->stream));
                 n++;
                 p += FK;
                 passes_in_batch++;
             } else {
-                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, arg_s0 >= 0, arg_s0, arg_s1};
+                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, T_start + p,
+                             arg_s0 >= 0, arg_s0, arg_s1};
                 CU(launch_single(a, d->force_sat != 0, d->stream));
                 p += 1;
             }
@@ -232,18 +237,20 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
             d->acs_launches_timed += n;
             d->acs_passes_timed += passes_in_batch;
         }
-        if (d->h_ctl->pos >= end) { pos = end; continue; }
+        const int done = (int)(d->h_ctl->T - T_start);
+        if (done >= end) { pos = end; continue; }
         // A pass declined to run: the reference's metrics are within 510*k of int16 saturation.
         // Do that stage with the exact saturating kernel and carry on from there.
-        pos = d->h_ctl->pos;
-        SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, pos, arg_s0 >= 0, arg_s0, arg_s1};
+        pos = done;
+        SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, pos, T_start + pos,
+                     arg_s0 >= 0, arg_s0, arg_s1};
         CU(launch_single(a, true, d->stream));
         d->launches++;
         if (sync_ctl(d)) return -1;
-        if (d->h_ctl->pos != pos + 1) { set_err("saturating stage did not run (pos %d)", d->h_ctl->pos); return -1; }
+        if (d->h_ctl->T != T_start + pos + 1) { set_err("saturating stage did not run (stage %lld)", d->h_ctl->T); return -1; }
         pos += 1;
     }
-    return d->h_ctl->renorm_count;
+    return d->h_ctl->renorm_count - ren_start;
 }
 
 int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
@@ -453,6 +460,83 @@ int v224x_update_dev(void *p, const unsigned char *dev_syms, int nbits)
     if (!d) return -1;
     if (bind(d)) return -1;
     return update_core(d, dev_syms, nbits);
+}
+
+// Advance several decoders (same device) by nbits stages each in lockstep: one persistent launch per batch over
+// all of them.  Returns 0 or -1; per-decoder renormalisation counts through renorms_out (may be NULL).
+int v224x_update_multi_dev(void **handles, const unsigned char *const *dev_syms, int nctx, int nbits, int *renorms_out)
+{
+    if (nctx < 1 || nctx > MAX_CTX || !handles || !dev_syms) { set_err("v224x_update_multi_dev: 1..%d decoders", MAX_CTX); return -1; }
+    Decoder *ds[MAX_CTX];
+    for (int s = 0; s < nctx; s++) {
+        ds[s] = as_dec(handles[s]);
+        if (!ds[s]) return -1;
+        if (ds[s]->dev != ds[0]->dev) { set_err("decoders must live on one device"); return -1; }
+        for (int t = 0; t < s; t++) if (ds[t] == ds[s]) { set_err("the same decoder was passed twice"); return -1; }
+    }
+    if (nbits <= 0) return 0;
+    Decoder *d0 = ds[0];
+    if (bind(d0)) return -1;
+    cudaStream_t st = d0->stream;
+    for (int s = 1; s < nctx; s++) CU(cudaStreamSynchronize(ds[s]->stream));
+    long long T_start[MAX_CTX];
+    int ren_start[MAX_CTX];
+    for (int s = 0; s < nctx; s++) {
+        T_start[s] = ds[s]->h_ctl->T;
+        ren_start[s] = ds[s]->h_ctl->renorm_count;
+        if (renorms_out) renorms_out[s] = 0;
+    }
+    constexpr int BATCH_STAGES = 8192;
+    const int fused_total = nbits / FK * FK;
+    int pos = 0;
+    bool lockstep = true;
+    while (lockstep && pos < fused_total) {
+        const int end = std::min(fused_total, pos + BATCH_STAGES);
+        const int npasses = (end - pos) / FK;
+        MultiArgs m;
+        m.nctx = nctx;
+        m.npasses = npasses;
+        for (int s = 0; s < nctx; s++) {
+            Decoder *d = ds[s];
+            if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
+            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->optab, d->len,
+                                   pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
+        }
+        if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
+        CU(launch_persist_multi(m, st));
+        if (d0->time_kernels) CU(cudaEventRecord(d0->kev1, st));
+        d0->launches += 2 * nctx + 1;
+        for (int s = 0; s < nctx; s++) {
+            Decoder *d = ds[s];
+            CU(cudaMemcpyAsync(d->h_ctl, d->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        if (d0->time_kernels) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, d0->kev0, d0->kev1));
+            d0->acs_ms += ms;
+            d0->acs_launches_timed += 2 * nctx + 1;
+            d0->acs_passes_timed += (unsigned long long)npasses * nctx;
+        }
+        for (int s = 0; s < nctx; s++) {
+            if (ds[s]->h_ctl->error) { set_err("device control block reports invariant violation %d", ds[s]->h_ctl->error); return -1; }
+            if (ds[s]->h_ctl->T - T_start[s] < end) lockstep = false;      // a decoder declined a pass: finish everyone one by one
+        }
+        pos = end;
+    }
+    // remainders (and the rare decoder that left lockstep) go through the single-decoder path, which resumes at ctl->pos
+    for (int s = 0; s < nctx; s++) {
+        Decoder *d = ds[s];
+        const int done = (int)(d->h_ctl->T - T_start[s]), ren = d->h_ctl->renorm_count - ren_start[s];
+        int r = 0;
+        if (done < nbits) {
+            // hand the decoder's own stream the rest; everything so far ran on d0's stream and is complete
+            r = update_core(d, dev_syms[s] + 2 * (size_t)done, nbits - done);
+            if (r < 0) return -1;
+        }
+        if (renorms_out) renorms_out[s] = ren + r;
+    }
+    return 0;
 }
 
 int v224x_stream_decode_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out)

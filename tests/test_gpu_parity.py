@@ -147,6 +147,40 @@ def test_block_stream_equals_per_bit_abi_loop():
     assert np.array_equal(blk[lag:], bits[:700 - lag])       # and they are the transmitted data
 
 
+def test_lockstep_multi_decoder_update_equals_separate_updates():
+    """v224x_update_multi_dev: three decoders with different streams (one of them mid-frame, one with a ragged
+    length) advanced by one persistent launch per batch == each advanced alone == the CPU checker."""
+    n = 203                                      # 25 fused passes + 3 single stages
+    streams = [S.vtest_frame(208, 1.0, seed=61)[1], S.telemetry_stream(208, 2.0, seed=62)[1], S.vtest_frame(208, 4.0, seed=63)[1]]
+    decs = [v224.Viterbi224(64 + 16 * i) for i in range(3)]
+    try:
+        dptr = []
+        for d, sy in zip(decs, streams):
+            p = d.dev_alloc(sy.size)
+            d.h2d(p, sy)
+            dptr.append(p)
+        decs[1].init(0x12345)
+        decs[1].update_blk(streams[1][:20], 10)          # decoder 1 starts the lockstep call mid-stream
+        want = []
+        for i, (d, sy) in enumerate(zip(decs, streams)):
+            with pyoracle.best_cpu_decoder()(d.len) as o:
+                if i == 1:
+                    o.init(0x12345)
+                    o.update_blk(sy[:20], 10)
+                r = o.update_blk(sy, n)
+                want.append((r, o.get_metrics(), [crc(o.get_row(k)) for k in range(d.len)], o.min_metric(), o.max_metric()))
+        ren = v224.Viterbi224.update_multi_dev(decs, dptr, n)
+        for i, d in enumerate(decs):
+            assert ren[i] == want[i][0]
+            assert np.array_equal(d.get_metrics(), want[i][1])
+            assert [crc(d.get_row(k)) for k in range(d.len)] == want[i][2]
+            assert (d.min_metric(), d.max_metric()) == (want[i][3], want[i][4])
+        assert decs[0].stats()["fused_passes"] == 25
+    finally:
+        for d in decs:
+            d.delete()
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference's own programs on our library (drop-in), and the vdecode mirror
 # ---------------------------------------------------------------------------------------------
