@@ -7,7 +7,9 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libviterbi224_b200.so")
-SOURCES = ["v224_kernels.cu", "v224_runtime.cu"]
+# (source, extra nvcc flags).  The fused ACS pass is compiled with ptxas -O1: at the default level ptxas reorders the
+# decision-bit gather behind a whole stage of butterflies and spills; in source order the tile body needs no spill.
+SOURCES = [("v224_acs_persist.cu", ["-Xptxas", "-O1"]), ("v224_kernels.cu", []), ("v224_runtime.cu", [])]
 HEADERS = ["v224_common.cuh", "v224_fused_core.cuh", "v224_kernels.h",
            os.path.join("..", "..", "include", "viterbi224.h"), os.path.join("..", "..", "include", "viterbi224_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -25,35 +27,45 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in [x[0] for x in SOURCES] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile the CUDA sources for sm_100a and link the shared library.  Returns its path."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, extra_flags=()):
+    """Compile the CUDA sources for sm_100a and link the shared library.  Returns its path.
+    out / extra_flags: A/B builds of kernel-shape variants into another file (tools/build_variants.sh)."""
+    variant = out is not None
+    if not variant and not force and not is_stale():
         return LIB
     nvcc = nvcc_path()
     objs = []
     log = []
-    for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", o, os.path.join(CSRC, s)]
+    for s, flags in SOURCES:
+        o = (out + "." if variant else os.path.join(CSRC, "")) + s.replace(".cu", ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *flags, *extra_flags, "-c", "-o", o, os.path.join(CSRC, s)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         objs.append(o)
-    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    lib = out if variant else LIB
+    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+    with open(lib + ".ptxas.log" if variant else os.path.join(CSRC, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
+    if variant:
+        for o in objs:
+            os.remove(o)
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "--out":
+        print(build_library(out=os.path.abspath(sys.argv[2]), extra_flags=sys.argv[3:]))
+    else:
+        print(build_library(force=True, verbose=True))

@@ -1,0 +1,566 @@
+// v224_acs_persist.cu -- the fused ACS pass of the B200 viterbi224 decoder (sm_100a).
+//
+//   k_acs_persist    8 trellis stages per HBM pass (viterbi224_sse2.c:264-328, x8); one launch runs many passes of
+//                    1..MAX_CTX independent decoders as a dataflow over a dynamic tile queue
+//   k_build_passtab  per-pass operand tables + ring rows
+//   k_persist_begin  launch prologue on the control block
+//
+// CTA = COMPUTE_WARPS compute warps + 1 protocol warp (warp specialisation).  The protocol warp runs the dataflow
+// one tile ahead of the compute warps: it claims the next (pass, decoder, tile) item, fetches the pass table, polls
+// the pass parameters and the previous pass's completion counters (all L2 round trips), and hands the tile over
+// through a shared-memory mbarrier; when the compute warps have issued a tile's stores it publishes the tile
+// (release) and, for the last tile of a pass, runs the resolver.  The compute warps therefore never wait for an
+// L2 round trip of the protocol, only for data.
+//
+// This file is compiled with -Xptxas -O1: at the default level ptxas hoists the decision-bit gather of a whole stage
+// behind the butterflies and spills (≈500 bytes per thread at 64 registers); in source order the tile body needs
+// no spill at all (see csrc/ptxas.log, profiles/).
+#include "v224_common.cuh"
+#include "v224_fused_core.cuh"
+#include "v224_kernels.h"
+
+namespace v224 {
+
+#ifdef V224_TRACE
+__device__ unsigned long long g_trace[64 * 1024 * 8];      // [pass < 64][tile][event]
+__device__ unsigned g_smid[64 * 1024];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(n, tau, ev) do { if ((threadIdx.x & 31) == 0 && (n) < 64) { g_trace[((n) * 1024 + (tau)) * 8 + (ev)] = gtime(); if ((ev) == 1) { unsigned sm_; asm volatile("mov.u32 %0, %smid;" : "=r"(sm_)); g_smid[(n) * 1024 + (tau)] = sm_; } } } while (0)
+#else
+#define TRACE(n, tau, ev) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_cs_v4(void *p, uint4 v)   // streaming store: decision rows are write-once
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_v2(void *p, uint32_t x, uint32_t y)
+{
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void st_v8(void *p, const uint32_t (&v)[8])   // 256-bit store (sm_100+)
+{
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel()
+{
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_acq_rel_add64(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+// shared-memory mbarriers (CTA scope)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bar_compute()     // the compute warps' own barrier (the protocol warp never joins)
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(FUSED_THREADS) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory of one CTA
+// ------------------------------------------------------------------------------------------
+struct TileInfo {
+    const uint16_t *oldm;
+    uint16_t *newm;
+    uint32_t *ring;
+    PassStats *st;
+    uint32_t tau;
+    uint32_t sub2;       // sub in both halves
+    int go;              // 1 run the tile, 0 skip it (decoder stopped), -1 no more work
+    int careful;
+    int n, s;            // pass and decoder (protocol warp's own bookkeeping)
+    int pad[2];
+};
+struct __align__(16) FusedSmem {
+    uint32_t tile[XCHG_BUFS][256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 (32 KiB each): round-1 -> round-2 exchange
+    uint32_t tab[2][PASSTAB_WORDS];                          // operand table + ring rows of the tile's pass
+    TileInfo info[2];
+    uint32_t s0[FK + 4];                                     // state-0 metric after each stage (meaningful in tile 0 only)
+    uint64_t full[2], done[2];                               // mbarriers: tile handed over / tile's stores issued
+};
+
+// Per-pass tables of a whole launch: the operand table from the pass's 8 symbol pairs, and the ring row of each
+// of its 8 stages ((T0 + 8*pass + t) mod len, done once here instead of per thread and stage).  The rows' format
+// tags are set here as well (only by the last stage of the launch that writes a given ring row).
+__global__ void __launch_bounds__(PASSTAB_WORDS) k_build_passtab(uint32_t *tab, const uint8_t *syms, int npasses, long long T0, int len,
+                                                                 uint8_t *row_fmt)
+{
+    const int pass = blockIdx.x, e = threadIdx.x;
+    if (pass >= npasses) return;
+    uint32_t v;
+    if (e < OPTAB_WORDS) {
+        v = optab_entry(e, syms + 2 * (size_t)pass * FK);
+    } else {
+        const int t = e - OPTAB_WORDS;
+        const long long stage = (long long)pass * FK + t;
+        v = (uint32_t)((T0 + stage) % len);
+        if (stage + len >= (long long)npasses * FK) row_fmt[v] = (uint8_t)(t + 1);
+    }
+    tab[(size_t)pass * PASSTAB_WORDS + e] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// compute warps: one tile, eight stages
+// ------------------------------------------------------------------------------------------
+template <int T, bool CAREFUL>
+__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *tab, uint32_t *s0, uint32_t *ring_chunk,
+                                            PassStats *st)
+{
+    uint32_t dw[NQ];
+    acs_stage<T>(A, pbase, tab, dw);
+    uint32_t *dst = ring_chunk + (size_t)tab[OPTAB_WORDS + T - 1] * ROWWORDS;
+    if (NQ == 4) st_cs_v4(dst, make_uint4(dw[0], dw[1], dw[NQ - 2], dw[NQ - 1]));
+    else         st_cs_v2(dst, dw[0], dw[1]);
+    if (threadIdx.x == 0) s0[T] = A[0][0] & 0xffffu;               // slot 0 (tile 0, thread 0) always holds state 0
+    if (CAREFUL && T < FK) {
+        uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
+        if ((threadIdx.x & 31) == 0) atomicMin(&st->minP[T][(blockIdx.x * (FUSED_THREADS / 32) + (threadIdx.x >> 5)) % STAT_BUCKETS][0], mn);
+    }
+}
+
+// shared-memory exchange element (row m, column group g): NQ words.  For NQ = 2 a half-warp of round 2 reads two
+// rows 16 apart (same banks): swap the 64-byte halves of the odd-mh rows so that the two rows land on disjoint banks.
+__device__ __forceinline__ uint32_t xchg_index(uint32_t m, uint32_t g)
+{
+    return NQ == 2 ? m * FUSED_COLGROUPS + (g ^ ((m >> 1) & 8u)) : m * FUSED_COLGROUPS + g;
+}
+
+// Tile `tau` = columns [64 tau, 64 tau + 64) of all 256 rows.  Metrics are read through L2 only (another SM wrote
+// them, possibly within this launch).  `xbuf` = this tile's exchange buffer.
+template <bool CAREFUL>
+__device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, int trace_n)
+{
+    const uint32_t tid = threadIdx.x, tau = ti.tau, sub = ti.sub2;
+    PassStats *st = ti.st;
+    uint32_t *ring_chunk = ti.ring + (size_t)(tau * FUSED_THREADS + tid) * NQ;      // see fused_bit_address()
+    uint32_t A[16][NQ];
+    {
+        // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 2*NQ columns ----
+        uint32_t thr, g;
+        round1_map(tid, thr, g);
+        const uint32_t G = tau * FUSED_COLGROUPS + g;              // global column group: columns COLW*G ..
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(ti.oldm) + ((size_t)thr * 32768 + (size_t)G * COLW) * 2;
+#pragma unroll
+        for (int mh = 0; mh < 16; mh++) {
+            if (NQ == 4) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)mh * 16 * 65536));
+                A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
+            } else {
+                const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(src + (size_t)mh * 16 * 65536));
+                A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+            }
+        }
+        TRACE(trace_n, tau, 2);
+        const uint32_t pbase = (thr << 15) | (G << COLW_LOG2);
+        fused_stage<1, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<2, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<3, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<4, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        // ---- exchange: rows m = mh*16 + ml ----
+        if (XCHG_BUFS == 1) bar_compute();                         // the previous tile's round-2 reads are over
+#pragma unroll
+        for (int mh = 0; mh < 16; mh++) {
+            const uint32_t e = xchg_index(mh * 16 + thr, g);
+            if (NQ == 4) reinterpret_cast<uint4 *>(xbuf)[e] = make_uint4(A[mh][0], A[mh][1], A[mh][NQ - 2], A[mh][NQ - 1]);
+            else         reinterpret_cast<uint2 *>(xbuf)[e] = make_uint2(A[mh][0], A[mh][1]);
+        }
+    }
+    bar_compute();
+    {
+        // ---- round 2: thread = (mh = thr, g); registers = 16 ml rows ----
+        uint32_t thr, g;
+        round2_map(tid, thr, g);
+        const uint32_t G = tau * FUSED_COLGROUPS + g;
+#pragma unroll
+        for (int ml = 0; ml < 16; ml++) {
+            const uint32_t e = xchg_index(thr * 16 + ml, g);
+            if (NQ == 4) {
+                const uint4 v = reinterpret_cast<const uint4 *>(xbuf)[e];
+                A[ml][0] = v.x; A[ml][1] = v.y; A[ml][NQ - 2] = v.z; A[ml][NQ - 1] = v.w;
+            } else {
+                const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
+                A[ml][0] = v.x; A[ml][1] = v.y;
+            }
+        }
+        TRACE(trace_n, tau, 3);
+        const uint32_t pbase = (thr << 19) | (G << COLW_LOG2);
+        fused_stage<5, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<6, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<7, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<8, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        TRACE(trace_n, tau, 4);
+        // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B, four lanes = one line ----
+        {
+            uint16_t *dst = ti.newm + ((size_t)(G * COLW) << 8) + thr * 16;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = __byte_perm(A[2 * i][q], A[2 * i + 1][q], h ? 0x7632 : 0x5410);
+                    st_v8(dst + ((q * 2 + h) << 8), w);
+                }
+            }
+        }
+        // ---- statistics of the final stage ----
+        {
+            const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
+            if ((tid & 31) == 0) {
+                const uint32_t b = (blockIdx.x * (FUSED_THREADS / 32) + (tid >> 5)) % STAT_BUCKETS;
+                atomicMin(&st->minP[FK][b][0], mn);
+                atomicMax(&st->maxP[b][0], mx);
+            }
+            __syncwarp();
+            if (tau == 0 && tid < FK) st->s0[tid + 1] = s0[tid + 1];          // tid 0 wrote them (same warp)
+        }
+        TRACE(trace_n, tau, 5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// protocol warp
+// ------------------------------------------------------------------------------------------
+constexpr unsigned SPIN_LIMIT = 20u * 1000u * 1000u;      // polls of >= 20-40 ns: seconds.  A wait that long means a broken invariant.
+
+__device__ __forceinline__ void slot_reset(PassSlot &s)
+{
+    stats_reset(s.st);
+    s.done_word = 0;
+}
+
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T)
+{
+    PersistCtl &pc = c->pc;
+    pc.next_item = 0;
+    pc.resolved_upto = 0;
+    pc.npasses = npasses;
+    pc.force_careful = force_careful;
+    pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
+    pc.maxR_prev = c->maxR;
+    for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i]); pc.slot[i].pass_word = 0; }
+    const int careful0 = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
+    const int careful1 = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
+    pc.slot[0].pass_word = make_pass_word(0, careful0, c->sub);
+    pc.slot[1].pass_word = make_pass_word(1, careful1, 0);
+    int stop = npasses;
+    if (c->spread > MAX_FAST_SPREAD || c->error || c->T != expected_T) stop = 0;
+    // non-careful passes are not validated stage by stage: keep them well away from saturation
+    if (!careful0 && c->maxR + 510ll * FK > 32767) stop = 0;
+    if (stop > 1 && !careful1 && c->maxR + 510ll * 2 * FK > 32767) stop = 1;
+    pc.stop_pass = stop;
+}
+
+// Resolve pass n (run by the protocol thread that completed the pass's last tile).  Replays the reference's
+// renormalisation test per stage, validates that the reference could not have saturated, commits
+// the pass (or invalidates it), and publishes the parameters of pass n+2.
+__device__ void resolve_persist(Ctl *c, int n)
+{
+    PersistCtl &pc = c->pc;
+    for (unsigned spins = 0; (int)ld_acquire(&pc.resolved_upto) != n;) {
+        __nanosleep(64);
+        if (++spins > SPIN_LIMIT) { atomicOr((unsigned *)&c->error, 16u); atomicMin(&pc.stop_pass, 0); return; }
+    }
+    PassSlot &sl = pc.slot[n % PSLOTS];
+    const unsigned long long pw = *(volatile unsigned long long *)&sl.pass_word;
+    const bool careful = (pw >> 31) & 1u;
+    const int sub = (int)(pw & 0x7fffffffu);
+    bool valid = !c->error && n < *(volatile int *)&pc.stop_pass;
+    long long O = pc.Ostore + sub;                     // offset of the values this pass loaded
+    long long maxR = pc.maxR_prev;                     // exact at pass start; +510 per stage bounds it inside
+    long long renormals = 0;
+    int count = 0;
+    for (int t = 1; valid && t <= FK; t++) {
+        // the adds of stage t clip in the reference iff some R + branch metric exceeds SHRT_MAX (:296-299)
+        if (maxR + 510 > 32767) { valid = false; break; }
+        maxR += 510;
+        const long long R0 = (long long)*(volatile unsigned *)&sl.st.s0[t] + O;
+        if (R0 >= RENORM_TRIGGER) {                                        // viterbi224_sse2.c:351
+            const unsigned mnt = stats_min(sl.st, t);
+            if (!(careful || t == FK) || mnt == 0xffffffffu) { c->error |= 1; valid = false; break; }
+            const long long minR = (long long)mnt + O;                    // :358-366
+            renormals += (minR < 0 ? minR + 65536 : minR) + 32768;        // :354,:366,:367 (uint16 read of the minimum)
+            count++;
+            O -= minR + 32768;                                             // :373
+            maxR -= minR + 32768;
+        }
+    }
+    const unsigned mn = stats_min(sl.st, FK), mx = stats_max(sl.st), z = *(volatile unsigned *)&sl.st.s0[FK];
+    if (valid && (mn == 0xffffffffu || mx < mn)) { c->error |= 2; valid = false; }
+    if (valid && (long long)mx - mn > MAX_FAST_SPREAD) valid = false;
+    if (valid) {
+        pc.Ostore = O;
+        pc.maxR_prev = (long long)mx + O;
+        c->renormals += renormals;
+        c->renorm_count += count;
+        // external view (what the host and the single-stage kernel see between launches)
+        c->sub = (int)mn;
+        c->O = O + mn;
+        c->R0 = (long long)z + O;
+        c->maxR = (long long)mx + O;
+        c->spread = (long long)mx - mn;
+        c->T += FK;
+        c->cur = (c->cur + 1) % NBUF;
+        c->n_fused++;
+        if (careful) c->n_careful++;
+        // parameters of pass n+2 (its slot is free: pass n-2 is long resolved)
+        PassSlot &nx = pc.slot[(n + 2) % PSLOTS];
+        slot_reset(nx);
+        const int sub1 = (int)(*(volatile unsigned long long *)&pc.slot[(n + 1) % PSLOTS].pass_word & 0x7fffffffu);
+        const int careful2 = pc.force_careful || ((long long)z + O + 510ll * 2 * FK >= RENORM_TRIGGER);
+        if (!careful2 && (long long)mx + O + 510ll * 2 * FK > 32767) {
+            if (n + 2 < pc.stop_pass) pc.stop_pass = n + 2;
+        }
+        __threadfence();                                                   // the reset slot before the word that opens it
+        *(volatile unsigned long long *)&nx.pass_word = make_pass_word(n + 2, careful2, (int)mn - sub1);   // sub <= min of pass n+1's output
+    } else {
+        // the pass (and anything that already consumed its output) is discarded; its input buffer is intact
+        if (n < pc.stop_pass) { pc.stop_pass = n; c->n_invalidated++; }
+    }
+    __threadfence();
+    st_release(&pc.resolved_upto, (unsigned)(n + 1));
+}
+
+// The protocol warp's loop.  Two tile slots (b = k & 1): while the compute warps run tile k, tile k+1 is prepared.
+//   prepare(k): claim an item, fetch its pass table, wait for pass parameters + dependencies, publish info[b], arrive full[b]
+//   signal(k) : once done[b] completes (every compute warp issued tile k's stores): release-add the pass's done word,
+//               resolve the pass if this was its last tile; slot b is free again
+// Signalling never queues behind a dependency wait (a tile this CTA still has to publish may be exactly what its
+// next tile depends on), so the loop polls both.
+__device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
+{
+    const unsigned lane = threadIdx.x & 31;
+    unsigned *queue = &m.ctx[0].ctl->pc.next_item;
+    const unsigned per_pass = (unsigned)m.nctx * FUSED_TILES;
+    unsigned k_prep = 0, k_sig = 0;        // tiles prepared / published so far
+    bool have_item = false, exiting = false;
+    unsigned item = 0, spins = 0;
+    int n = 0;
+    unsigned s = 0, tau = 0;
+
+    for (;;) {
+        bool progress = false;
+        // ---- publish finished tiles ----
+        if (k_sig < k_prep && mbar_test(&sm.done[k_sig & 1], (k_sig >> 1) & 1)) {
+            const TileInfo &ti = sm.info[k_sig & 1];
+            if (ti.go > 0 && lane == 0) {
+                Ctl *c = m.ctx[ti.s].ctl;
+                PassSlot &sl = c->pc.slot[ti.n % PSLOTS];
+                // release: the compute warps' stores (ordered before this thread by the mbarrier) become visible GPU-wide
+                // before the tile counts as done
+                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(ti.tau % TILE_CLASSES));
+                TRACE(ti.n, ti.tau, 6);
+                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, ti.n);
+                TRACE(ti.n, ti.tau, 7);
+            }
+            __syncwarp();
+            k_sig++;
+            progress = true;
+        }
+        if (exiting) {
+            if (k_sig == k_prep) break;
+        } else if (k_prep - k_sig < 2) {
+            // ---- prepare the next tile ----
+            const unsigned b = k_prep & 1;
+            if (!have_item) {
+                if (lane == 0) item = atomicAdd(queue, 1u);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                n = (int)(item / per_pass);
+                const unsigned r = item % per_pass, w = r % FUSED_TILES;
+                s = r / FUSED_TILES;
+                tau = (w % 256u) * TILE_CLASSES + w / 256u;        // a pass emits its tile classes in turn
+                have_item = true;
+                spins = 0;
+                if (n < m.npasses) {
+                    TRACE(n, tau, 0);
+                    // the pass table does not depend on anything that is still running
+                    const uint4 *src = reinterpret_cast<const uint4 *>(m.ctx[s].passtab + (size_t)n * PASSTAB_WORDS);
+                    for (unsigned e = lane; e < PASSTAB_WORDS / 4; e += 32) reinterpret_cast<uint4 *>(sm.tab[b])[e] = __ldcg(src + e);
+                }
+            }
+            if (n >= m.npasses) {
+                // no more work: tell the compute warps (they leave without arriving on done[b], so this slot is not a tile)
+                if (lane == 0) sm.info[b].go = -1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.full[b]);
+                exiting = true;
+                progress = true;
+            } else {
+                const PersistArgs &a = m.ctx[s];
+                PersistCtl &pc = a.ctl->pc;
+                // one round of parallel loads: pass parameters, stop mark, the previous pass's completion counters
+                unsigned long long v = 0;
+                if (lane == 0) v = ld_relaxed64(&pc.slot[n % PSLOTS].pass_word);
+                if (lane == 1) v = ld_relaxed(&pc.stop_pass);
+                if (lane == 2 && n > 0) v = ld_relaxed64(&pc.slot[(n - 1) % PSLOTS].done_word);
+                const unsigned long long pw = __shfl_sync(0xffffffffu, v, 0);
+                const int stop = (int)(unsigned)__shfl_sync(0xffffffffu, v, 1);
+                const unsigned long long dwd = __shfl_sync(0xffffffffu, v, 2);
+                bool stopped = n >= stop;
+                // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
+                const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) && (n == 0 || done_class_count(dwd, tau >> 8) >= 256u);
+                if (!stopped && !ready && ++spins > SPIN_LIMIT) {
+                    if (lane == 0) { atomicOr((unsigned *)&a.ctl->error, 16u); atomicMin(&pc.stop_pass, 0); }
+                    stopped = true;
+                }
+                if (stopped || ready) {
+                    fence_acq_rel();                           // acquire: the producers' metric stores, the pass parameters
+                    if (lane == 0) {
+                        TileInfo &ti = sm.info[b];
+                        const int cur = (a.cur0 + n) % NBUF;    // buffers advance by one per resolved pass
+                        ti.oldm = a.metrics[cur];
+                        ti.newm = a.metrics[(cur + 1) % NBUF];
+                        ti.ring = a.ring;
+                        ti.st = &pc.slot[n % PSLOTS].st;
+                        ti.tau = tau;
+                        ti.sub2 = (uint32_t)(pw & 0x7fffffffu) * 0x10001u;
+                        ti.careful = (int)((pw >> 31) & 1u);
+                        ti.go = stopped ? 0 : 1;
+                        ti.n = n;
+                        ti.s = (int)s;
+                        TRACE(n, tau, 1);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.full[b]);
+                    k_prep++;
+                    have_item = false;
+                    progress = true;
+                }
+            }
+        }
+        if (!progress) __nanosleep(20);
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_persist(MultiArgs m)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1);
+        mbar_init(&sm.done[0], FUSED_THREADS / 32); mbar_init(&sm.done[1], FUSED_THREADS / 32);
+    }
+    __syncthreads();
+    if (tid >= FUSED_THREADS) {
+        protocol_warp(sm, m);
+        return;
+    }
+    for (unsigned k = 0;; k++) {
+        const unsigned b = k & 1;
+        mbar_wait(&sm.full[b], (k >> 1) & 1);
+        const TileInfo &ti = sm.info[b];
+        const int go = ti.go;
+        if (go < 0) break;
+        if (go > 0) {
+            uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? b : 0];
+            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, ti.n);
+            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, ti.n);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.done[b]);      // this warp's stores of tile k are issued; it is done with slot b
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------
+size_t passtab_bytes(int npasses) { return (size_t)npasses * PASSTAB_WORDS * sizeof(uint32_t); }
+
+// One persistent launch over m.nctx decoders x m.npasses passes (+ one table build and one begin kernel per decoder).
+cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int checked[64], slots[64];
+    if (dev >= 0 && dev < 64 && !checked[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, FUSED_THREADS + 32, sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        slots[dev] = per_sm * sms;
+        checked[dev] = 1;
+    }
+    for (int s = 0; s < m.nctx; s++) {
+        const PersistArgs &a = m.ctx[s];
+        k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
+        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0);
+    }
+    const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
+    const int grid = (int)(items < slots[dev] ? items : slots[dev]);
+    k_acs_persist<<<grid, FUSED_THREADS + 32, sizeof(FusedSmem), st>>>(m);
+    return cudaGetLastError();
+}
+
+} // namespace v224
+
+#ifdef V224_TRACE
+extern "C" int v224_debug_read_trace(unsigned long long *host, unsigned long long n)
+{
+    return (int)cudaMemcpyFromSymbol(host, v224::g_trace, n * sizeof(unsigned long long));
+}
+extern "C" int v224_debug_read_smid(unsigned *host, unsigned long long n)
+{
+    return (int)cudaMemcpyFromSymbol(host, v224::g_smid, n * sizeof(unsigned));
+}
+#endif

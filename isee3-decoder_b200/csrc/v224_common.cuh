@@ -31,20 +31,33 @@ constexpr long long MAX_FAST_SPREAD = 24000;
 // Fused pass geometry: FK stages per HBM pass, done as two register rounds of FR stages.
 constexpr int FR = 4;
 constexpr int FK = 2 * FR;                         // 8 trellis stages per pass
-// Tile width.  64 columns (512 tiles of 128 threads, 4 CTAs/SM) measured 17.3 us per pass on B200,
-// 32 columns (1024 tiles of 64 threads, 8 CTAs/SM: better balanced, 7 vs 6 tiles per SM) 19.2 us:
-// the finer tiles lose more to per-tile overhead than they gain in balance (profiles/).
-#ifndef V224_TILE_COLS_LOG2
-#define V224_TILE_COLS_LOG2 6
+// A tile is all 256 rows (m) x 64 consecutive columns (j) of the [256][2^15] view of the metric array (32 KiB).
+// A thread holds 16 rows x NQ packed registers (2*NQ columns).  NQ = 2: 256 threads per tile at <= 64 registers,
+// 4 tiles = 32 warps per SM (default).  NQ = 4: 128 threads per tile at 128 registers, 16 warps per SM -- the
+// first-generation shape, kept as a build option for A/B runs (profiles/).
+#ifndef V224_NQ
+#define V224_NQ 2
 #endif
-constexpr int FUSED_COLS_LOG2 = V224_TILE_COLS_LOG2;
+constexpr int NQ = V224_NQ;                        // packed 2x16-bit registers per row per thread
+static_assert(NQ == 2 || NQ == 4, "columns per thread");
+constexpr int COLW_LOG2 = NQ == 2 ? 2 : 3;         // log2(columns per thread)
+constexpr int COLW = 1 << COLW_LOG2;
+constexpr int FUSED_COLS_LOG2 = 6;
 constexpr int FUSED_TILE_COLS = 1 << FUSED_COLS_LOG2;  // columns (j) per tile
-constexpr int FUSED_COLGROUPS = FUSED_TILE_COLS / 8;   // 8 columns (4 packed registers) per thread
-constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column groups
-constexpr int FUSED_CTAS_PER_SM = 512 / FUSED_THREADS; // 16 warps per SM at 128 registers
-constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // tiles per pass
+constexpr int FUSED_COLGROUPS = FUSED_TILE_COLS / COLW; // column groups (one per thread column) per tile: 16 / 8
+constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column groups: 256 / 128
+// CTA = FUSED_THREADS compute threads + one protocol warp (v224_acs_persist.cu).  3 CTAs of 288 threads per SM at 72
+// registers; the round-1 -> round-2 exchange buffer is double-buffered when shared memory allows (3 x 67 KiB).
+#ifndef V224_CTAS_PER_SM
+#define V224_CTAS_PER_SM 3
+#endif
+constexpr int FUSED_CTAS_PER_SM = V224_CTAS_PER_SM;
+#ifndef V224_XCHG_BUFS
+#define V224_XCHG_BUFS (V224_CTAS_PER_SM <= 3 ? 2 : 1)
+#endif
+constexpr int XCHG_BUFS = V224_XCHG_BUFS;
+constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512 tiles per pass
 constexpr int TILE_CLASSES    = 128 / FUSED_TILE_COLS; // tile t of pass n+1 reads the tiles == (t >> 8) mod TILE_CLASSES of pass n
-static_assert(FUSED_TILE_COLS == 32 || FUSED_TILE_COLS == 64, "tile width");
 
 // Path-metric buffers rotate A -> B -> C -> A.  Three (not two) so that, in the persistent kernel,
 // pass n+1 may already be writing while pass n is still being validated: pass n's input stays
@@ -94,19 +107,24 @@ __host__ __device__ inline unsigned stats_max(const PassStats &s)
     return m;
 }
 
-// Bookkeeping of one in-flight pass of the persistent kernel.
+// Bookkeeping of one in-flight pass of the persistent kernel.  Two 64-bit words carry everything a tile's protocol
+// warp has to poll, so that one round of parallel loads decides "may this tile start":
+//   done_word = [63:48] class-1 tiles done | [47:32] class-0 tiles done | [31:0] tiles done   (class = tile index mod 2)
+//   pass_word = (pass number + 1) << 32 | careful << 31 | sub     published by the resolver of pass n-2 (or the launch)
 struct PassSlot {
     PassStats st;
-    unsigned done[TILE_CLASSES];   // finished tiles by (tile index mod TILE_CLASSES): what the next pass waits on
-    unsigned done_total;
-    int sub;                // what this pass subtracts from every P while loading
-    int careful;            // this pass records per-stage minima
+    unsigned long long done_word;
+    unsigned long long pass_word;
 };
+__host__ __device__ inline unsigned long long make_pass_word(int n, int careful, int sub)
+{
+    return ((unsigned long long)(unsigned)(n + 1) << 32) | ((unsigned long long)(careful ? 1u : 0u) << 31) | (unsigned)sub;
+}
+__host__ __device__ inline unsigned done_class_count(unsigned long long w, unsigned cls) { return (unsigned)(w >> (32 + 16 * cls)) & 0xffffu; }
+__host__ __device__ inline unsigned long long done_increment(unsigned cls) { return 1ull | (1ull << (32 + 16 * cls)); }
+static_assert(TILE_CLASSES == 2, "done_word layout");
 struct PersistCtl {
     unsigned next_item;     // dynamic work queue head: item = pass * 512 + order index
-    unsigned next_rank;     // balanced mode: SM ranks handed out in arrival order
-    int sm_rank[256];       // balanced mode: rank of SM %smid (-1 until its first CTA arrives)
-    unsigned sm_slots[256]; // balanced mode: CTAs that arrived on SM %smid
     unsigned resolved_upto; // number of passes resolved (in order)
     int stop_pass;          // passes >= stop_pass must not run (saturation watch / invalidated pass)
     int npasses;
@@ -138,50 +156,49 @@ struct Ctl {
 };
 constexpr size_t CTL_HOST_BYTES = offsetof(Ctl, st);
 
-// ---- tile partitions of the 4096 column groups (8 columns each) -------------------------------
-// UNIFORM: tile t = groups [t*CG, (t+1)*CG), CG = FUSED_COLGROUPS.
-// BALANCED (B200, 148 SMs x 4 CTAs): every SM gets 14 or 13 warps' worth of work instead of 16 or 12:
-//   SM rank r < 124 owns 28 consecutive groups as tiles of 8,8,6,6; rank r >= 124 owns 26 as 8,6,6,6
-//   (124*28 + 24*26 = 4096).  A tile of 6 groups uses 3 warps of its CTA, one of 8 groups all 4.
-constexpr int BAL_SMS = 148, BAL_CTAS_PER_SM = 4, BAL_BIG_SMS = 124, BAL_TILES = BAL_SMS * BAL_CTAS_PER_SM;
-__host__ __device__ inline void balanced_tile(uint32_t rank, uint32_t slot, uint32_t &g0, uint32_t &ncg)
+// ---- thread <-> (row group, column group) maps of the two register rounds --------------------
+// Round 1 (stages 1-4): thread = (ml, g), a warp = 32/CG row groups x CG column groups: every 64/128-bit load
+// instruction reads whole 128-byte lines.  Round 2 (stages 5-8): thread = (mh, g), a warp = 4 row groups x 8
+// column groups, so that the 32-byte metric stores of four lanes make one 128-byte line.
+__host__ __device__ inline void round1_map(uint32_t tid, uint32_t &thr, uint32_t &g)
 {
-    const bool big = rank < BAL_BIG_SMS;
-    const uint32_t base = big ? rank * 28u : BAL_BIG_SMS * 28u + (rank - BAL_BIG_SMS) * 26u;
-    if (big) { ncg = slot < 2 ? 8u : 6u; g0 = base + (slot < 2 ? slot * 8u : 16u + (slot - 2) * 6u); }
-    else     { ncg = slot < 1 ? 8u : 6u; g0 = base + (slot < 1 ? 0u : 8u + (slot - 1) * 6u); }
+    thr = tid / FUSED_COLGROUPS;
+    g = tid % FUSED_COLGROUPS;
 }
-// the balanced tile that contains column group G
-__host__ __device__ inline void balanced_tile_of_group(uint32_t G, uint32_t &g0, uint32_t &ncg)
+__host__ __device__ inline void round2_map(uint32_t tid, uint32_t &thr, uint32_t &g)
 {
-    uint32_t rank, r;
-    if (G < BAL_BIG_SMS * 28u) { rank = G / 28u; r = G % 28u; balanced_tile(rank, r < 8 ? 0 : r < 16 ? 1 : r < 22 ? 2 : 3, g0, ncg); }
-    else { const uint32_t Gp = G - BAL_BIG_SMS * 28u; rank = BAL_BIG_SMS + Gp / 26u; r = Gp % 26u; balanced_tile(rank, r < 8 ? 0 : r < 14 ? 1 : r < 20 ? 2 : 3, g0, ncg); }
+    const uint32_t w = tid >> 5, lane = tid & 31;
+    thr = (w / (FUSED_COLGROUPS / 8)) * 4 + (lane >> 3);
+    g = (w % (FUSED_COLGROUPS / 8)) * 8 + (lane & 7);
+}
+__host__ __device__ inline uint32_t round2_tid(uint32_t thr, uint32_t g)
+{
+    const uint32_t w = (thr >> 2) * (FUSED_COLGROUPS / 8) + (g >> 3), lane = ((thr & 3) << 3) | (g & 7);
+    return (w << 5) | lane;
 }
 
-// Decision-row formats: 0 = canonical; t (1..8) = stage t of a pass over UNIFORM tiles; 8 + t = over BALANCED tiles.
-constexpr uint8_t ROWFMT_BALANCED = 8;
-
-// where a fused-format decision bit lives: fmt as above, state s after that stage.
-// Returns the bit index inside the 2^23-bit row.  Slot fields (23 bits): mh[4] | ml[4] | G[12] | q[2] | h[1];
-// a thread (row group thr, column group G) of tile (g0, ncg) owns the 16-byte chunk g0*16 + thr*ncg + (G - g0).
+// Decision-row formats: 0 = canonical; t (1..8) = written by stage t of a fused pass.
+// Where a fused-format decision bit lives: state s after stage t -> bit index inside the 2^23-bit row.
+// Slot fields (23 bits): mh[4] | ml[4] | j[15], j = tile[9] | g | q | h.  The thread (tile, tid) owns the NQ
+// consecutive words starting at word (tile * FUSED_THREADS + tid) * NQ; inside them
+//   word = side * NQ/2 + q/2, byte = (q & 1) * 2 + h, bit = pair index
+// where `inner` is the 4-bit row index a thread holds in that round (mh in round 1, ml in round 2), the stage's
+// butterfly pairs the two rows that differ in bit sb of `inner`, side = that bit, pair index = the other three.
 __host__ __device__ inline uint32_t fused_bit_address(int fmt, uint32_t s)
 {
-    const int t = fmt > ROWFMT_BALANCED ? fmt - ROWFMT_BALANCED : fmt;
-    // slot p = state rotated right by t (the slot its survivor sits in during the pass)
-    uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;
-    uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, G = (p >> 3) & 4095;
-    uint32_t q = (p >> 1) & 3, h = p & 1;
-    uint32_t g0, ncg;
-    if (fmt > ROWFMT_BALANCED) balanced_tile_of_group(G, g0, ncg);
-    else { ncg = FUSED_COLGROUPS; g0 = G - G % FUSED_COLGROUPS; }
-    uint32_t thr   = (t <= FR) ? ml : mh;       // thread row-group in this round
-    uint32_t inner = (t <= FR) ? mh : ml;       // register row index in this round
-    uint32_t chunk = g0 * 16 + thr * ncg + (G - g0);              // 16-byte chunk per thread
-    uint32_t w     = inner >> 2;                                  // word in chunk
-    uint32_t i     = ((inner & 3) << 1) | (q >> 1);               // bit in byte
-    uint32_t byte  = ((q & 1) << 1) | h;                          // byte in word
-    return chunk * 128 + w * 32 + byte * 8 + i;
+    const int t = fmt;
+    uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;      // the slot its survivor sits in during the pass
+    const uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, j = p & 32767;
+    const uint32_t tile = j >> FUSED_COLS_LOG2, g = (j & (FUSED_TILE_COLS - 1)) >> COLW_LOG2;
+    const uint32_t q = (j & (COLW - 1)) >> 1, h = j & 1;
+    const bool r1 = t <= FR;
+    const uint32_t inner = r1 ? mh : ml;
+    const uint32_t tid = r1 ? ml * FUSED_COLGROUPS + g : round2_tid(mh, g);
+    const int sb = FR - 1 - ((t - 1) % FR);
+    const uint32_t side = (inner >> sb) & 1;
+    const uint32_t pidx = ((inner >> (sb + 1)) << sb) | (inner & ((1u << sb) - 1));
+    const uint32_t word = (tile * FUSED_THREADS + tid) * NQ + side * (NQ / 2) + (q >> 1);
+    return word * 32 + (((q & 1) << 1) | h) * 8 + pidx;
 }
 
 } // namespace v224

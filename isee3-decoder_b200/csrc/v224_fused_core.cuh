@@ -13,7 +13,7 @@
 //   memory once.  After 8 stages slot (m, j) holds state (j << 8) | m.
 //
 //   Two columns j, j+1 share one 32-bit register (packed 16-bit metrics); both halves run the
-//   same butterfly with their own branch metric.
+//   same butterfly with their own branch metric.  A thread holds NQ such registers per row.
 //
 // Branch metrics: for the butterfly whose bit-0 member sits in slot p (stage bit cleared) the
 // expected symbols are parity(reg24 & POLYn) with reg24 = rotl^(t-1)(p) << 1 (viterbi224_sse2.c
@@ -98,8 +98,10 @@ template <int T> V224_HD uint32_t slot_label(uint32_t p)
 }
 constexpr uint32_t FLIP_LABEL = (uint32_t)G1FLIP | ((uint32_t)G2FLIP << 1);
 
-// Operand table in shared memory: optab[(t-1)*32 + beta*8 + {0..3: X[beta^i], 4..7: K[beta^i]}]
+// Operand table in shared memory: optab[(t-1)*32 + beta*8 + {0..3: X[beta^i], 4..7: K[beta^i]}].
+// The per-pass table in global memory (PassTab) carries it plus the ring rows of the pass's eight stages.
 constexpr int OPTAB_WORDS = FK * 32;
+constexpr int PASSTAB_WORDS = OPTAB_WORDS + FK;      // 264 words = 66 x 16 bytes
 
 // Entry `e` (0 .. FK*32) of the operand table for the pass whose symbols are sym[2*(t-1)], sym[2*(t-1)+1].
 template <typename SymPtr>
@@ -119,13 +121,13 @@ V224_HD uint32_t optab_entry(int e, SymPtr sym)
     return (uint32_t)(0x8000 - d_lo) | ((uint32_t)(0x8000 - d_hi) << 16);
 }
 
-// One trellis stage over a thread's 16 rows x 4 packed registers.
-//   A[inner][q]  : packed P metrics, halves = columns 2q, 2q+1 of the thread's 8 columns
+// One trellis stage over a thread's 16 rows x NQ packed registers.
+//   A[inner][q]  : packed P metrics, halves = columns 2q, 2q+1 of the thread's 2*NQ columns
 //   pbase        : the thread's slot bits outside (inner, q, h)
 //   optab        : shared operand table
-//   dw[4]        : returns the 128 decision bits of this thread/stage in fused layout
+//   dw[NQ]       : returns the 32*NQ decision bits of this thread/stage in fused layout (fused_bit_address())
 template <int T>
-V224_HD void acs_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *optab, uint32_t (&dw)[4])
+V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *optab, uint32_t (&dw)[NQ])
 {
     constexpr int sb = FR - 1 - ((T - 1) % FR);          // stage bit inside `inner`
     constexpr int ishift = (T <= FR) ? 19 : 15;           // slot position of `inner`
@@ -134,14 +136,15 @@ V224_HD void acs_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *opt
     uint32_t Xv[4], Kv[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { Xv[i] = tab[i]; Kv[i] = tab[4 + i]; }
-    dw[0] = dw[1] = dw[2] = dw[3] = 0;
 #pragma unroll
-    for (int ia = 0; ia < 16; ia++) {
-        if ((ia >> sb) & 1) continue;
+    for (int w = 0; w < NQ; w++) dw[w] = 0;
+#pragma unroll
+    for (int pidx = 0; pidx < 8; pidx++) {
+        const int ia = ((pidx >> sb) << (sb + 1)) | (pidx & ((1 << sb) - 1));
         const int ic = ia | (1 << sb);
-        uint32_t D0[4], D1[4];
+        uint32_t D0[NQ], D1[NQ];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NQ; q++) {
             const uint32_t off = ((uint32_t)ia << ishift) | ((uint32_t)q << 1);
             const uint32_t c = slot_label<T>(off);
             const uint32_t X = Xv[c], Y = Xv[c ^ 3], K0 = Kv[c], K1 = Kv[c ^ 3];
@@ -150,40 +153,41 @@ V224_HD void acs_stage(uint32_t (&A)[16][4], uint32_t pbase, const uint32_t *opt
             const uint32_t t0 = cc + Y, t1 = cc + X;
             // decision0 = m0 > m1  <=>  (c - a) - delta < 0  <=> bit15 of D0 clear   (:316)
             // decision1 = m2 > m3  <=>  (c - a) + delta < 0  <=> bit15 of D1 clear   (:317)
-            D0[q] = cc - a + K0;
-            D1[q] = cc - a + K1;
+            const uint32_t u = cc - a;
+            D0[q] = u + K0;
+            D1[q] = u + K1;
             A[ia][q] = f_addmin_u16x2(a, X, t0);          // min(m0, m1) -> state 2b    (:319)
             A[ic][q] = f_addmin_u16x2(a, Y, t1);          // min(m2, m3) -> state 2b+1  (:320)
         }
-        // gather the (inverted) sign bits: byte = (q&1)*2 + half, bit-in-byte = (inner&3)*2 + q/2
+        // gather the (inverted) sign bits: word = side * NQ/2 + q/2, byte = (q&1)*2 + half, bit = pair index
 #pragma unroll
-        for (int qq = 0; qq < 2; qq++) {
+        for (int qq = 0; qq < NQ / 2; qq++) {
             const uint32_t s0 = f_prmt(D0[2 * qq], D0[2 * qq + 1], 0xfdb9);
             const uint32_t s1 = f_prmt(D1[2 * qq], D1[2 * qq + 1], 0xfdb9);
-            dw[ia >> 2] = (~s0 & (0x01010101u << (((ia & 3) << 1) | qq))) | dw[ia >> 2];
-            dw[ic >> 2] = (~s1 & (0x01010101u << (((ic & 3) << 1) | qq))) | dw[ic >> 2];
+            dw[qq] = (~s0 & (0x01010101u << pidx)) | dw[qq];
+            dw[NQ / 2 + qq] = (~s1 & (0x01010101u << pidx)) | dw[NQ / 2 + qq];
         }
     }
 }
 
 // packed min / max over a thread's 64 registers
-V224_HD uint32_t tile_min(const uint32_t (&A)[16][4])
+V224_HD uint32_t tile_min(const uint32_t (&A)[16][NQ])
 {
     uint32_t m = A[0][0];
 #pragma unroll
     for (int i = 0; i < 16; i++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) m = f_minu2(m, A[i][q]);
+        for (int q = 0; q < NQ; q++) m = f_minu2(m, A[i][q]);
     uint32_t lo = m & 0xffff, hi = m >> 16;
     return lo < hi ? lo : hi;
 }
-V224_HD uint32_t tile_max(const uint32_t (&A)[16][4])
+V224_HD uint32_t tile_max(const uint32_t (&A)[16][NQ])
 {
     uint32_t m = A[0][0];
 #pragma unroll
     for (int i = 0; i < 16; i++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) m = f_maxu2(m, A[i][q]);
+        for (int q = 0; q < NQ; q++) m = f_maxu2(m, A[i][q]);
     uint32_t lo = m & 0xffff, hi = m >> 16;
     return lo > hi ? lo : hi;
 }

@@ -4,26 +4,13 @@
 
 namespace v224 {
 
-struct FusedArgs {
-    Ctl *ctl;
-    uint16_t *metrics[NBUF];
-    uint32_t *ring;
-    uint8_t *row_fmt;
-    const uint8_t *syms;     // device symbols of the running update call (2 per bit)
-    uint32_t *optab;         // scratch: this pass's operand table (256 words)
-    int len;                 // ring rows
-    int expected_pos;        // index of this pass's first symbol pair in syms
-    long long expected_T;    // the control block's stage counter this launch was issued for (else it declines)
-    int force_careful;       // test knob: record per-stage minima regardless
-};
-
 struct PersistArgs {
     Ctl *ctl;
     uint16_t *metrics[NBUF];
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;     // symbols of the running update call; this launch starts at stage pos0
-    uint32_t *optab;         // npasses x 256 words, filled by k_build_optab at launch
+    uint32_t *passtab;       // npasses x PASSTAB_WORDS words (operand table + ring rows), filled by k_build_passtab at launch
     int len;
     int pos0;                // stages of this call already done when the launch starts
     int cur0;                // metric buffer holding the launch's input
@@ -32,8 +19,8 @@ struct PersistArgs {
     int force_careful;
 };
 
-// Several independent decoders advanced in lockstep by ONE persistent launch (dynamic queue only): while the tiles
-// of one decoder's pass drain, the CTAs already work on the next decoder's pass, so nobody waits at a pass boundary.
+// 1..MAX_CTX independent decoders advanced in lockstep by ONE persistent launch: while the tiles of one decoder's
+// pass drain, the CTAs already work on another decoder's pass, so nobody waits at a pass boundary.
 constexpr int MAX_CTX = 4;
 struct MultiArgs {
     int nctx;
@@ -61,9 +48,8 @@ struct TraceArgs {
 };
 
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
-cudaError_t launch_fused(const FusedArgs &a, cudaStream_t st);
-cudaError_t launch_persist(const PersistArgs &a, int mode, cudaStream_t st);
-cudaError_t launch_persist_multi(const MultiArgs &m, cudaStream_t st);
+cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st);
+size_t passtab_bytes(int npasses);
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

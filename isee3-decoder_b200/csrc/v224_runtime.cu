@@ -95,7 +95,7 @@ struct Decoder {
     Ctl *ctl;
     Ctl *h_ctl;                 // pinned mirror, refreshed at the end of every update
     uint8_t *dsyms; size_t dsyms_cap;
-    uint32_t *optab; size_t optab_cap;     // per-pass operand tables of the running batch
+    uint32_t *optab; size_t optab_cap;     // per-pass tables (operands + ring rows) of the running batch
     uint8_t *dout;  size_t dout_cap;       // chainback / stream output staging
     uint32_t *seg;  size_t seg_cap;        // chainback segment bookkeeping
     unsigned *d_redo;
@@ -105,7 +105,7 @@ struct Decoder {
     int *d_flag;
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, tile_mode, chain_seg, chain_warm;
+    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     double acs_ms;
@@ -199,32 +199,29 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         unsigned long long n = 0;
         int p = pos;
         const bool fuse = !d->force_single && !d->force_sat;
-        if (fuse && !d->per_pass_launch && end - p >= FK) {
-            // one persistent launch runs all full passes of this batch as a dataflow
-            const int npasses = (end - p) / FK;
-            if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
-            PersistArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
-                          d->h_ctl->cur, T_start + p, npasses, d->force_careful};
-            CU(launch_persist(a, d->tile_mode, d->stream));
-            p += npasses * FK;
-            n += 3;
-            passes_in_batch = npasses;
+        if (fuse && end - p >= FK) {
+            // one persistent launch runs all full passes of this batch as a dataflow ("per_pass_launch": one launch per pass)
+            const int total = (end - p) / FK;
+            const int per_launch = d->per_pass_launch ? 1 : total;
+            if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(per_launch))) return -1;
+            for (int done_p = 0; done_p < total; done_p += per_launch) {
+                const int npasses = std::min(per_launch, total - done_p);
+                MultiArgs m;
+                m.nctx = 1;
+                m.npasses = npasses;
+                m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
+                                       (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
+                CU(launch_persist(m, d->stream));
+                p += npasses * FK;
+                n += 3;
+            }
+            passes_in_batch = total;
         }
         while (p < end) {
-            if (fuse && d->per_pass_launch && end - p >= FK) {
-                if (grow((void **)&d->optab, &d->optab_cap, 1024)) return -1;
-                FusedArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p, T_start + p,
-                            d->force_careful};
-                CU(launch_fused(a, d->stream));
-                n++;
-                p += FK;
-                passes_in_batch++;
-            } else {
-                SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, T_start + p,
-                             arg_s0 >= 0, arg_s0, arg_s1};
-                CU(launch_single(a, d->force_sat != 0, d->stream));
-                p += 1;
-            }
+            SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, T_start + p,
+                         arg_s0 >= 0, arg_s0, arg_s1};
+            CU(launch_single(a, d->force_sat != 0, d->stream));
+            p += 1;
             n++;
         }
         if (d->time_kernels) CU(cudaEventRecord(d->kev1, d->stream));
@@ -297,7 +294,6 @@ void *create_viterbi224(int len)
     d->magic = MAGIC;
     d->dev = dev;
     d->len = len;
-    d->tile_mode = -1;
     d->chain_seg = 128;
     d->chain_warm = 256;
     d->ring_bytes = (size_t)len * ROWBYTES;
@@ -498,12 +494,12 @@ int v224x_update_multi_dev(void **handles, const unsigned char *const *dev_syms,
         m.npasses = npasses;
         for (int s = 0; s < nctx; s++) {
             Decoder *d = ds[s];
-            if (grow((void **)&d->optab, &d->optab_cap, (size_t)npasses * 1024)) return -1;
+            if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
             m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->optab, d->len,
                                    pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
         }
         if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
-        CU(launch_persist_multi(m, st));
+        CU(launch_persist(m, st));
         if (d0->time_kernels) CU(cudaEventRecord(d0->kev1, st));
         d0->launches += 2 * nctx + 1;
         for (int s = 0; s < nctx; s++) {
@@ -731,7 +727,6 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
-    else if (!strcmp(key, "tile_mode")) d->tile_mode = (int)value;      // -1 best, 0 dynamic queue, 1 static, 2 balanced
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

@@ -47,7 +47,7 @@ def test_golden_default_path(golden_cases, name):
 
 
 @pytest.mark.parametrize("opts", [{"force_single": 1}, {"force_sat": 1}, {"force_careful": 1}, {"per_pass_launch": 1},
-                                  {"per_pass_launch": 1, "force_careful": 1}, {"tile_mode": 0}, {"tile_mode": 1}, {"tile_mode": 2},
+                                  {"per_pass_launch": 1, "force_careful": 1},
                                   {"chain_seg": 8, "chain_warm": 0},
                                   {"chain_seg": 64, "chain_warm": 16}])
 @pytest.mark.parametrize("name", ["awgn1db_648_chunks", "erasure_304", "ringwrap_len40_200", "saturation_forced_72", "stream_d64_320"])

@@ -11,7 +11,6 @@ n = 64 * 8
 bits, syms = v224.streams.telemetry_stream(n, 3.0, seed=5)
 static = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 with v224.Viterbi224(n) as d:
-    d.set_option("tile_mode", static)
     d.init(0); d.update_blk(syms, n)
     d.init(0); d.update_blk(syms, n)
     tr = np.zeros(64 * 1024 * 8, dtype=np.uint64)
@@ -22,7 +21,8 @@ with v224.Viterbi224(n) as d:
     lib.v224_debug_read_smid.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong]
     assert lib.v224_debug_read_smid(smid.ctypes.data_as(ctypes.c_void_p), smid.size) == 0
 smid = smid.reshape(64, 1024)
-tr = tr.reshape(64, 1024, 8).astype(np.int64)
+tr = tr.reshape(64, 1024, 8).astype(np.int64)[:, :512]
+smid = smid[:, :512]
 names = ["claim", "dep ok", "loads landed", "exchange done", "round2 done", "stores issued", "fence done", "signalled"]
 print("static" if static else "dynamic", "tiles; times in us relative to the pass's first 'dep ok'")
 for p in range(20, 28):
@@ -42,7 +42,7 @@ r1 = 1e-3 * (t[:, 3] - t[:, 2])
 tot = 1e-3 * (t[:, 6] - t[:, 1])
 import collections
 by = collections.defaultdict(list)
-for tile in range(1024):
+for tile in range(512):
     by[int(smid[p, tile])].append(tile)
 hist = collections.Counter(len(v) for v in by.values())
 print("  SMs by number of active tiles:", dict(sorted(hist.items())), " SMs used:", len(by))
