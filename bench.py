@@ -5,13 +5,14 @@
 
 One "step" = one complete decode of a 1,048,576-bit (1024 minor frames) symdemod-format soft-symbol
 stream through the streaming path of vdecode.c (update + decodebit(delay=200, state 0) per bit,
-vdecode.c:145-152) in block form: 131072 fused 8-stage ACS passes (128 persistent launches of 1024 passes) + batched tracebacks.  The
+vdecode.c:145-152) in block form: 131072 fused 8-stage ACS passes + batched tracebacks, run as 3 contiguous segments by 3 decoders that one persistent
+kernel advances in lockstep (every hand-over between segments verified on the device, output identical to the sequential decode).  The
 sync-correlator phase flip (vdecode.c:107-140) is host logic and runs once, before the timed region.
 
   value : whole-job decoded bits/s with the symbol pairs resident in HBM (device events, max over ranks)
   e2e   : the same through the host-buffer C-ABI call v224x_stream_decode (pinned host memory,
           H2D of the symbols and D2H of the decoded bits inside the timed region)
-  roofline : dominant kernel k_acs_fused -- algorithmic bytes per launch (2*16 MiB metrics + 8 MiB
+  roofline : dominant kernel k_acs_persist -- algorithmic bytes per launch (2*16 MiB metrics + 8 MiB
           decisions + 16 symbol bytes) / mean launch duration from CUDA events on the library's stream
   cpu_baseline : the reference's own SSE2 decoder (oracle/_ref, compiled from the unmodified sources) on
           all host cores, one independent stream prefix per core, timed in the same run (rank 0, N=1)
@@ -37,6 +38,8 @@ NBITS = 1 << 20                 # bits per GPU per step ("1M bits", 1024 minor f
 DELAY = 200                     # vdecode default decode delay (vdecode.c:44)
 BLOCK = 8192                    # stages per update batch; ring = BLOCK + DELAY rows (8.2 GiB)
 WARMUP_STAGES = 2048            # leading warm-up of mid-stream segments (N > 1)
+SEGMENTS = 3                    # per GPU: decoders advanced in lockstep over contiguous segments of the rank's stream
+CONV = 2048                     # stages a late-started decoder gets to converge before its verified hand-over
 EBN0_DB = 3.0
 SEED = 20141
 FK = 8
@@ -181,10 +184,10 @@ def run_reference_sample(sample_bits, threads):
     return threads * sample_bits / dt, kind, dt
 
 
-def acs_passes_extra(launches, passes):
-    """Each persistent launch is preceded by two small bookkeeping kernels (k_build_optab, k_persist_begin) that are
-    inside the timed ACS region but move ~1 KiB per pass: two thirds of the timed launches."""
-    return 2 * (launches // 3) if passes >= launches else 0
+def persistent_launches(launches, nseg):
+    """Each persistent launch over nseg decoders is preceded by two small bookkeeping kernels per decoder
+    (k_build_passtab, k_persist_begin) that are inside the timed ACS region but move ~1 KiB per pass."""
+    return max(1, launches // (2 * nseg + 1))
 
 
 def host_threads():
@@ -223,7 +226,9 @@ def workload_config(n):
                         f"{NBITS} bits (1024 minor frames) per GPU, Eb/N0 {EBN0_DB} dB, decode delay {DELAY}, automatic symbol-phase flip "
                         "(odd junk prefix on rank 0)",
             "bits_per_gpu": NBITS, "decode_delay": DELAY, "stages_per_pass": FK, "block_stages": BLOCK,
-            "parallelism": f"time-segmented x{n}, warm-up {WARMUP_STAGES} stages" if n > 1 else "single GPU",
+            "parallelism": (f"time-segmented x{n} GPUs, warm-up {WARMUP_STAGES} stages; " if n > 1 else "single GPU; ")
+                           + f"per GPU {SEGMENTS} decoders in lockstep over contiguous segments, hand-overs verified on the device "
+                             f"(warm-up {DELAY}+{CONV} stages each)",
             "cache": "decision ring 8.2 GiB per GPU is written once per stage and is far larger than the 126 MB L2; the two 16 MiB "
                      "path-metric buffers are re-read by the next pass by construction (no artificial L2 flush possible without "
                      "changing the algorithm)"}
@@ -236,6 +241,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--segments", type=int, default=SEGMENTS, help="decoders advanced in lockstep per GPU (1 = sequential)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -272,21 +278,32 @@ def main():
     hp_bits = lib.v224x_host_alloc_pinned(n)
     ctypes.memmove(hp_syms, wl["pairs"].ctypes.data, 2 * n)
 
+    nseg = max(1, args.segments)
+    seg_rep = {}
+
     def step_device():
         dec.init(0) if rank == 0 else dec.init_uniform(5000, -1)
-        return dec.stream_decode_dev(dsyms, n, DELAY, dbits)
+        seg_rep.update(dec.stream_decode_seg_dev(dsyms, n, DELAY, dbits, nseg, CONV))
 
     def step_e2e():
         dec.init(0) if rank == 0 else dec.init_uniform(5000, -1)
-        r = lib.v224x_stream_decode(dec.h, hp_syms, n, DELAY, hp_bits)
+        rep = v224.binding.SegReport()
+        r = lib.v224x_stream_decode_seg(dec.h, hp_syms, n, DELAY, hp_bits, nseg, CONV, ctypes.byref(rep))
         assert r >= 0, lib.v224x_last_error()
         return r
+
+    # ---------------- reference output of this rank: the sequential block decode (untimed) ----------------
+    dec.init(0) if rank == 0 else dec.init_uniform(5000, -1)
+    dec.stream_decode_dev(dsyms, n, DELAY, dbits)
+    out_seq = np.empty(n, np.uint8)
+    dec.d2h(out_seq, dbits)
 
     # ---------------- value leg: inputs resident in HBM ----------------
     for _ in range(args.warmup):
         step_device()
     out = np.empty(n, np.uint8)
     dec.d2h(out, dbits)
+    seg_same = bool(np.array_equal(out, out_seq))
     errs, nchk = ber_check(out, wl)
     dec.kernel_time_enable(True)
     l0 = dec.stats()["launches"]
@@ -327,6 +344,7 @@ def main():
 
     if rank == 0:
         peak, peak_src, _ = peaks()
+        nseg_used = int(seg_rep.get("segments", 1))
         value = bits_total * args.steps / (ms_dev_max * 1e-3)
         e2e = bits_total * args.steps / (ms_e2e_max * 1e-3)
         achieved = (B_PASS * acs_passes / (acs_ms * 1e-3)) / 1e9 if acs_ms > 0 else None      # GB/s, this rank's kernel
@@ -334,8 +352,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "fused_traffic.json")
         if os.path.exists(tp):
             per_pass = json.load(open(tp)).get("dram_bytes_per_pass")
-            launches_real = max(1, acs_launches - acs_passes_extra(acs_launches, acs_passes))
-            traffic = per_pass * acs_passes / launches_real if per_pass else None      # per launch, like `achieved`
+            traffic = per_pass * acs_passes / persistent_launches(acs_launches, nseg_used) if per_pass else None      # per launch, like `achieved`
         line = {"metric": "decoded_bits_per_s", "value": value, "unit": "bits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
                 "data": "synthetic", "config": workload_config(world),
@@ -345,12 +362,13 @@ def main():
                 "gpu_launches": int(launches_total),
                 "roofline": {"bound": "hbm", "kernel": "k_acs_persist", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_pass": B_PASS, "passes_per_launch": acs_passes / max(1, acs_launches - acs_passes_extra(acs_launches, acs_passes)),
-                             "algorithmic_bytes_per_launch": B_PASS * acs_passes / max(1, acs_launches - acs_passes_extra(acs_launches, acs_passes)),
+                             "algorithmic_bytes_per_pass": B_PASS, "passes_per_launch": acs_passes / persistent_launches(acs_launches, nseg_used),
+                             "algorithmic_bytes_per_launch": B_PASS * acs_passes / persistent_launches(acs_launches, nseg_used),
                              "launches_timed": acs_launches, "passes_timed": acs_passes, "mean_pass_us": 1e3 * acs_ms / max(1, acs_passes),
                              "frac_unfused_equivalent": value / world * B_STAGE_UNFUSED / 1e9 / peak},
                 "clocks": clocks,
                 "check": {"bit_errors_vs_transmitted": int(errs_total), "bits_checked": int(nchk_total), "phase_flips_rank0": wl["flips"],
+                          "segmented_output_identical_to_sequential_rank0": seg_same, "segments_rank0": seg_rep,
                           "wall_ms_per_step": wall_max / args.steps,
                           "passes": {k: st[k] for k in ("fused_passes", "careful_passes", "single_stages", "sat_stages")}}}
         if world == 1 and not args.no_cpu_baseline:

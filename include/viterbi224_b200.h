@@ -46,6 +46,28 @@ int v224x_update_dev(void *p, const unsigned char *dev_syms, int nbits);
  * the state nctx separate v224x_update_dev() calls would leave.  renorms_out[i] (optional) = decoder i's return value. */
 int v224x_update_multi_dev(void **handles, const unsigned char *const *dev_syms, int nctx, int nbits, int *renorms_out);
 
+/* v224x_stream_decode with the stream cut into nseg (1..4) contiguous segments that nseg decoders on this GPU
+ * advance in lockstep (one persistent kernel works through all of them, so no SM idles at a decoder's pass
+ * boundary).  The handle continues its current state over the first segment; each further decoder starts
+ * delay + conv stages early from uniform metrics (conv < 0: 2048).  bits_out is ALWAYS what v224x_stream_decode
+ * returns: every hand-over is checked on the device (the two decoders' path-metric vectors must differ by a
+ * constant `delay` stages before the later one's first output -- from there on their decisions are identical),
+ * and when a check fails the rest of the stream is decoded again sequentially.  After the call the handle holds
+ * the end-of-stream state up to a constant metric offset: further stream/decodebit calls continue exactly, while
+ * update return values and min/max metrics are relative to that offset.  Returns 0, -1 on error. */
+typedef struct {
+    int segments;            /* segments used (1 = stream too short: plain sequential decode)          */
+    int warm;                /* warm-up stages of every segment but the first (delay + conv)           */
+    int verified;            /* hand-over checks that passed                                           */
+    int redone;              /* segments decoded again sequentially because a check failed             */
+    long long extra_stages;  /* trellis stages run on top of nbits (warm-ups + redone segments)        */
+    int worst_spread;        /* largest (max - min) metric difference seen at a check (0 = converged)  */
+} v224x_seg_report;
+int v224x_stream_decode_seg(void *p, const unsigned char *syms, int nbits, int delay, unsigned char *bits_out, int nseg, int conv,
+                            v224x_seg_report *report);
+int v224x_stream_decode_seg_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out, int nseg,
+                                int conv, v224x_seg_report *report);
+
 /* init variant for time-segmented decoding: every metric = SHRT_MIN + bias and no state is
  * favoured (start_state < 0), or init_viterbi224 semantics (start_state >= 0). */
 int v224x_init_uniform(void *p, int bias, int start_state);

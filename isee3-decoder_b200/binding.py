@@ -14,7 +14,7 @@ ABI_SYMBOLS = ["create_viterbi224", "init_viterbi224", "update_viterbi224_blk", 
                "decodebit_viterbi224", "decodeword_viterbi224", "max_metric_viterbi224", "min_metric_viterbi224",
                "delete_viterbi224"]
 EXT_SYMBOLS = ["v224x_device_count", "v224x_set_device", "v224x_last_error", "v224x_version", "v224x_stream_decode",
-               "v224x_stream_decode_dev", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
+               "v224x_stream_decode_dev", "v224x_stream_decode_seg", "v224x_stream_decode_seg_dev", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
                "v224x_h2d", "v224x_d2h", "v224x_host_alloc_pinned", "v224x_host_free_pinned", "v224x_timer_start",
                "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms", "v224x_kernel_time_passes",
                "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option"]
@@ -29,6 +29,11 @@ class Stats(ctypes.Structure):
                 ("single_stages", ctypes.c_ulonglong), ("sat_stages", ctypes.c_ulonglong), ("invalidated_passes", ctypes.c_ulonglong),
                 ("chainback_redo", ctypes.c_ulonglong),
                 ("renormals", ctypes.c_longlong), ("stages", ctypes.c_longlong)]
+
+
+class SegReport(ctypes.Structure):
+    _fields_ = [("segments", ctypes.c_int), ("warm", ctypes.c_int), ("verified", ctypes.c_int), ("redone", ctypes.c_int),
+                ("extra_stages", ctypes.c_longlong), ("worst_spread", ctypes.c_int)]
 
 
 def library_path():
@@ -64,6 +69,8 @@ def load_library():
         "v224x_version": (ctypes.c_char_p, []),
         "v224x_stream_decode": (ci, [vp, vp, ci, ci, vp]),
         "v224x_stream_decode_dev": (ci, [vp, vp, ci, ci, vp]),
+        "v224x_stream_decode_seg": (ci, [vp, vp, ci, ci, vp, ci, ci, vp]),
+        "v224x_stream_decode_seg_dev": (ci, [vp, vp, ci, ci, vp, ci, ci, vp]),
         "v224x_update_dev": (ci, [vp, vp, ci]),
         "v224x_update_multi_dev": (ci, [vp, vp, ci, ci, vp]),
         "v224x_init_uniform": (ci, [vp, ci, ci]),
@@ -180,6 +187,23 @@ class Viterbi224:
         out = np.empty(n, dtype=np.uint8)
         r = self._check(self.lib.v224x_stream_decode(self.h, p, n, int(delay), out.ctypes.data_as(ctypes.c_void_p)), "v224x_stream_decode")
         return out, r
+
+    def stream_decode_seg(self, syms, delay, nseg, conv=-1, nbits=None):
+        """v224x_stream_decode_seg: the stream in nseg segments advanced in lockstep, hand-overs verified on the device.
+        Returns (bits uint8[nbits], report dict)."""
+        a, p = _u8(syms)
+        n = a.size // 2 if nbits is None else int(nbits)
+        out = np.empty(n, dtype=np.uint8)
+        rep = SegReport()
+        self._check(self.lib.v224x_stream_decode_seg(self.h, p, n, int(delay), out.ctypes.data_as(ctypes.c_void_p), int(nseg), int(conv),
+                                                     ctypes.byref(rep)), "v224x_stream_decode_seg")
+        return out, {k: getattr(rep, k) for k, _ in SegReport._fields_}
+
+    def stream_decode_seg_dev(self, dev_syms, nbits, delay, dev_bits, nseg, conv=-1):
+        rep = SegReport()
+        self._check(self.lib.v224x_stream_decode_seg_dev(self.h, dev_syms, int(nbits), int(delay), dev_bits, int(nseg), int(conv),
+                                                         ctypes.byref(rep)), "v224x_stream_decode_seg_dev")
+        return {k: getattr(rep, k) for k, _ in SegReport._fields_}
 
     def dev_alloc(self, nbytes):
         p = self.lib.v224x_dev_alloc(self.h, int(nbytes))

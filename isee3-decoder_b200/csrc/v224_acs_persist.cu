@@ -397,6 +397,8 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
     for (;;) {
         bool progress = false;
         // ---- publish finished tiles ----
+        // Nothing else to do (next tile already handed over, or no more work): sleep on the mbarrier instead of polling it.
+        if (k_sig < k_prep && (k_prep - k_sig == 2 || exiting)) mbar_wait(&sm.done[k_sig & 1], (k_sig >> 1) & 1);
         if (k_sig < k_prep && mbar_test(&sm.done[k_sig & 1], (k_sig >> 1) & 1)) {
             const TileInfo &ti = sm.info[k_sig & 1];
             if (ti.go > 0 && lane == 0) {
@@ -484,7 +486,7 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
                 }
             }
         }
-        if (!progress) __nanosleep(20);
+        if (!progress) __nanosleep(k_sig < k_prep ? 40 : 100);    // a running tile to watch for / only dependencies to wait for
     }
 }
 

@@ -316,6 +316,25 @@ __global__ void __launch_bounds__(256) k_minmax(const uint16_t *m, unsigned *mnm
     if ((threadIdx.x & 31) == 0) { atomicMin(&mnmx[0], mn); atomicMax(&mnmx[1], mx); }
 }
 
+// Hand-over check of the segmented stream decode: two decoders make identical decisions from here on iff their
+// path-metric vectors differ by a constant.  out[0] = min, out[1] = max of a[s] - b[s] over all states.
+__global__ void __launch_bounds__(256) k_metric_diff(const uint16_t *a, const uint16_t *b, int *out)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 va = __ldcg(reinterpret_cast<const uint4 *>(a) + gid), vb = __ldcg(reinterpret_cast<const uint4 *>(b) + gid);
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    int mn = 0x7fffffff, mx = -0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int d = (int)((wa[e >> 1] >> ((e & 1) * 16)) & 0xffff) - (int)((wb[e >> 1] >> ((e & 1) * 16)) & 0xffff);
+        mn = min(mn, d);
+        mx = max(mx, d);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], mn); atomicMax(&out[1], mx); }
+}
+
 // Test hook: one decision row in the reference's canonical layout.
 __global__ void __launch_bounds__(256) k_export_row(TraceArgs a, long long row, uint32_t *out)
 {
@@ -405,6 +424,14 @@ cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st)
     cudaError_t e = cudaMemcpyAsync(mnmx, init, sizeof init, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     k_minmax<<<NSTATES / 8 / 256, 256, 0, st>>>(m, mnmx);
+    return cudaGetLastError();
+}
+cudaError_t launch_metric_diff(const uint16_t *a, const uint16_t *b, int *out2, cudaStream_t st)
+{
+    const int init[2] = {0x7fffffff, -0x7fffffff};
+    cudaError_t e = cudaMemcpyAsync(out2, init, sizeof init, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_metric_diff<<<NSTATES / 8 / 256, 256, 0, st>>>(a, b, out2);
     return cudaGetLastError();
 }
 cudaError_t launch_export_row(const TraceArgs &a, long long row, uint32_t *out, cudaStream_t st)

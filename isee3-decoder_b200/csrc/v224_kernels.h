@@ -58,6 +58,7 @@ cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t en
 cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st);
 cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st);
 cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st);
+cudaError_t launch_metric_diff(const uint16_t *a, const uint16_t *b, int *out2, cudaStream_t st);
 cudaError_t launch_export_row(const TraceArgs &a, long long row, uint32_t *out, cudaStream_t st);
 cudaError_t launch_export_metrics(const uint16_t *m, const Ctl *c, int16_t *out, int *range_error, cudaStream_t st);
 cudaError_t launch_import_metrics(uint16_t *m, const int16_t *in, Ctl *c, unsigned *mnmx, long long renormals, long long T, cudaStream_t st);

@@ -103,6 +103,10 @@ struct Decoder {
     unsigned *d_mnmx;
     unsigned long long *d_result, *h_result;   // walk results (pinned host copy)
     int *d_flag;
+    // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
+    struct Decoder *aux[MAX_CTX - 1];
+    uint16_t *snap;
+    int *d_segdiff;            // [2 * MAX_CTX]: min / max of the metric difference at each hand-over check
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
     int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm;
@@ -149,6 +153,7 @@ int sync_ctl(Decoder *d)
 void destroy(Decoder *d)
 {
     if (!d) return;
+    for (int i = 0; i < MAX_CTX - 1; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
     cudaSetDevice(d->dev);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
@@ -156,7 +161,7 @@ void destroy(Decoder *d)
     cudaFree(d->row_fmt); cudaFree(d->ctl);
     cudaFree(d->optab);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
-    cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag);
+    cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag); cudaFree(d->snap); cudaFree(d->d_segdiff);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
     if (d->h_result) cudaFreeHost(d->h_result);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -250,6 +255,72 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
     return d->h_ctl->renorm_count - ren_start;
 }
 
+// Lockstep update of nctx decoders on ds[0]'s stream (everything they did before must be complete or on that stream).
+int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nctx, int nbits, int *renorms_out)
+{
+    Decoder *d0 = ds[0];
+    cudaStream_t st = d0->stream;
+    long long T_start[MAX_CTX];
+    int ren_start[MAX_CTX];
+    for (int s = 0; s < nctx; s++) {
+        T_start[s] = ds[s]->h_ctl->T;
+        ren_start[s] = ds[s]->h_ctl->renorm_count;
+        if (renorms_out) renorms_out[s] = 0;
+    }
+    constexpr int BATCH_STAGES = 8192;
+    const int fused_total = nbits / FK * FK;
+    int pos = 0;
+    bool lockstep = true;
+    for (int s = 0; s < nctx; s++) if (ds[s]->force_single || ds[s]->force_sat) lockstep = false;
+    while (lockstep && pos < fused_total) {
+        const int end = std::min(fused_total, pos + BATCH_STAGES);
+        const int npasses = (end - pos) / FK;
+        MultiArgs m;
+        m.nctx = nctx;
+        m.npasses = npasses;
+        for (int s = 0; s < nctx; s++) {
+            Decoder *d = ds[s];
+            if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
+            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->optab, d->len,
+                                   pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
+        }
+        if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
+        CU(launch_persist(m, st));
+        if (d0->time_kernels) CU(cudaEventRecord(d0->kev1, st));
+        d0->launches += 2 * nctx + 1;
+        for (int s = 0; s < nctx; s++) {
+            Decoder *d = ds[s];
+            CU(cudaMemcpyAsync(d->h_ctl, d->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        if (d0->time_kernels) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, d0->kev0, d0->kev1));
+            d0->acs_ms += ms;
+            d0->acs_launches_timed += 2 * nctx + 1;
+            d0->acs_passes_timed += (unsigned long long)npasses * nctx;
+        }
+        for (int s = 0; s < nctx; s++) {
+            if (ds[s]->h_ctl->error) { set_err("device control block reports invariant violation %d", ds[s]->h_ctl->error); return -1; }
+            if (ds[s]->h_ctl->T - T_start[s] < end) lockstep = false;      // a decoder declined a pass: finish everyone one by one
+        }
+        pos = end;
+    }
+    // remainders (and the rare decoder that left lockstep) go through the single-decoder path, which resumes at the decoder's stage counter
+    for (int s = 0; s < nctx; s++) {
+        Decoder *d = ds[s];
+        const int done = (int)(d->h_ctl->T - T_start[s]), ren = d->h_ctl->renorm_count - ren_start[s];
+        int r = 0;
+        if (done < nbits) {
+            // the decoder's own stream takes the rest; everything so far ran on d0's stream and is complete
+            r = update_core(d, dev_syms[s] + 2 * (size_t)done, nbits - done);
+            if (r < 0) return -1;
+        }
+        if (renorms_out) renorms_out[s] = ren + r;
+    }
+    return 0;
+}
+
 int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
 {
     if (delay <= 0 || delay >= d->len) { set_err("stream decode needs 0 < delay < len (delay %d, len %d)", delay, d->len); return -1; }
@@ -267,6 +338,127 @@ int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8
     }
     CU(cudaStreamSynchronize(d->stream));
     return renorms;
+}
+
+// stream_core on another decoder of the same call: its own stream, after everything queued on `st` so far.
+int stream_core_on(Decoder *h, cudaStream_t st, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
+{
+    CU(cudaStreamSynchronize(st));
+    return stream_core(h, dev_syms, nbits, delay, dev_bits);
+}
+
+// Exchange everything but identity (the handle address the caller holds, the list of auxiliary decoders, options).
+void swap_bodies(Decoder *d, Decoder *o)
+{
+    Decoder td = *d, to = *o;
+    *d = to;
+    *o = td;
+    for (int i = 0; i < MAX_CTX - 1; i++) { d->aux[i] = td.aux[i]; o->aux[i] = nullptr; }
+    d->d_segdiff = td.d_segdiff; o->d_segdiff = to.d_segdiff;
+    d->force_single = td.force_single; d->force_sat = td.force_sat; d->force_careful = td.force_careful;
+    d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm;
+    d->time_kernels = td.time_kernels; d->acs_ms = td.acs_ms; d->acs_launches_timed = td.acs_launches_timed;
+    d->acs_passes_timed = td.acs_passes_timed; d->launches = td.launches;
+    o->time_kernels = to.time_kernels; o->acs_ms = to.acs_ms; o->acs_launches_timed = to.acs_launches_timed;
+    o->acs_passes_timed = to.acs_passes_timed; o->launches = to.launches;
+}
+
+// ---- segmented stream decode -----------------------------------------------------------------
+// One stream, nseg contiguous segments, nseg decoders advanced in lockstep by the persistent kernel (the CTAs that
+// would wait at one decoder's pass boundary work on another decoder's tiles).  Decoder 0 (the caller's handle)
+// continues its current state over segment 0; decoder i >= 1 starts W = delay + conv stages before its segment from
+// uniform metrics.  A decoder started late makes the same decisions as the sequential one from the stage at which
+// the two path-metric vectors differ by a constant.  That is CHECKED, not assumed: decoder i's metrics `conv`
+// stages after its start are compared with decoder i-1's metrics at the same stream position (`delay` stages
+// before decoder i's first output, so that every row its walks touch lies after the check).  If a check fails,
+// the stream from that segment on is decoded again sequentially by the last exact decoder.  The output therefore
+// always equals v224x_stream_decode's.
+Decoder *make_aux(Decoder *d)
+{
+    const int saved = g_device;
+    g_device = d->dev;
+    Decoder *a = static_cast<Decoder *>(create_viterbi224(d->len));
+    g_device = saved;
+    if (a) { a->force_careful = d->force_careful; a->per_pass_launch = d->per_pass_launch; }
+    return a;
+}
+
+int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits, int nseg, int conv, v224x_seg_report *rep)
+{
+    if (delay <= 0 || delay >= d->len) { set_err("stream decode needs 0 < delay < len (delay %d, len %d)", delay, d->len); return -1; }
+    if (conv < 0) conv = 2048;
+    const int W = delay + conv;                          // warm-up of segments 1..
+    int S = std::max(1, std::min(nseg, MAX_CTX));
+    constexpr int MIN_SEG = 4096;                        // not worth a warm-up below this
+    while (S > 1 && (long long)nbits < (long long)S * (W + MIN_SEG)) S--;
+    if (rep) { rep->segments = S; rep->warm = S > 1 ? W : 0; rep->verified = 0; rep->redone = 0; rep->extra_stages = 0; rep->worst_spread = 0; }
+    if (S == 1) return stream_core(d, dev_syms, nbits, delay, dev_bits);
+
+    const int A = ((nbits - W) / S) & ~7;                 // lockstep length of a segment's own range
+    const int Ltot = A + W;                               // local stages every decoder runs in lockstep
+    Decoder *D[MAX_CTX] = {d};
+    const uint8_t *sy[MAX_CTX];
+    long long T0[MAX_CTX];
+    for (int i = 1; i < S; i++) {
+        if (!d->aux[i - 1]) d->aux[i - 1] = make_aux(d);
+        D[i] = d->aux[i - 1];
+        if (!D[i]) { set_err("segmented decode: cannot create decoder %d of %d: %s", i, S, g_err); return -1; }
+        if (!D[i]->snap && cudaMalloc(&D[i]->snap, METRICBYTES) != cudaSuccess) { set_err("segmented decode: snapshot allocation failed"); cudaGetLastError(); return -1; }
+        if (do_init(D[i], INIT_BIAS, -1)) return -1;      // uniform metrics: no state is favoured
+    }
+    if (!d->d_segdiff) CU(cudaMalloc(&d->d_segdiff, 2 * MAX_CTX * sizeof(int)));
+    for (int i = 0; i < S; i++) {
+        sy[i] = dev_syms + 2 * (size_t)i * A;             // decoder i runs stream stages [i*A, i*A + Ltot)
+        T0[i] = D[i]->h_ctl->T;
+        CU(cudaStreamSynchronize(D[i]->stream));
+    }
+    cudaStream_t st = d->stream;
+    const int chunk_max = d->len - delay;
+    const int check_early = conv, check_late = Ltot - delay;       // local stage of the two sides of a hand-over check
+    int a = 0;
+    while (a < Ltot) {
+        int b = std::min(Ltot, a + chunk_max);
+        if (a < check_early && b > check_early) b = check_early;
+        if (a < check_late && b > check_late) b = check_late;
+        const uint8_t *sp[MAX_CTX];
+        for (int i = 0; i < S; i++) sp[i] = sy[i] + 2 * (size_t)a;
+        if (multi_update_core(D, sp, S, b - a, nullptr)) return -1;
+        for (int i = 0; i < S; i++) {
+            const int o0 = std::max(a, i ? W : 0);        // decoder i >= 1 emits nothing inside its warm-up
+            if (o0 < b) {
+                CU(launch_stream_trace(trace_args(D[i]), T0[i] + o0, b - o0, delay, dev_bits + (size_t)i * A + o0, st));
+                d->launches++;
+            }
+        }
+        if (b == check_early)
+            for (int i = 1; i < S; i++) CU(cudaMemcpyAsync(D[i]->snap, D[i]->metrics[D[i]->h_ctl->cur], METRICBYTES, cudaMemcpyDeviceToDevice, st));
+        if (b == check_late)
+            for (int i = 0; i + 1 < S; i++) {
+                CU(launch_metric_diff(D[i]->metrics[D[i]->h_ctl->cur], D[i + 1]->snap, d->d_segdiff + 2 * i, st));
+                d->launches++;
+            }
+        a = b;
+    }
+    int diff[2 * MAX_CTX];
+    CU(cudaMemcpyAsync(diff, d->d_segdiff, sizeof(int) * 2 * (S - 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int head = S - 1;                                     // the decoder that holds the exact state at the end of its range
+    for (int i = 0; i + 1 < S; i++) {
+        const int spread = diff[2 * i + 1] - diff[2 * i];
+        if (rep && spread > rep->worst_spread) rep->worst_spread = spread;
+        if (spread != 0) { head = i; break; }             // decoder i+1 had not converged: everything after decoder i is redone
+        if (rep) rep->verified++;
+    }
+    // the tail: what is left after the lockstep part, or -- after a failed check -- everything from decoder `head`'s end
+    const int done_upto = (head + 1) * A + W;              // stream stages decoded exactly so far
+    if (rep) { rep->redone = S - 1 - head; rep->extra_stages = (long long)(S - 1) * W + (long long)(S - 1 - head) * A; }
+    if (done_upto < nbits) {
+        Decoder *h = D[head];
+        if (stream_core_on(h, st, dev_syms + 2 * (size_t)done_upto, nbits - done_upto, delay, dev_bits + done_upto) < 0) return -1;
+    }
+    CU(cudaStreamSynchronize(st));
+    if (head != 0) swap_bodies(d, D[head]);               // the caller's handle continues the stream from its end
+    return 0;
 }
 
 } // namespace
@@ -471,68 +663,9 @@ int v224x_update_multi_dev(void **handles, const unsigned char *const *dev_syms,
         for (int t = 0; t < s; t++) if (ds[t] == ds[s]) { set_err("the same decoder was passed twice"); return -1; }
     }
     if (nbits <= 0) return 0;
-    Decoder *d0 = ds[0];
-    if (bind(d0)) return -1;
-    cudaStream_t st = d0->stream;
+    if (bind(ds[0])) return -1;
     for (int s = 1; s < nctx; s++) CU(cudaStreamSynchronize(ds[s]->stream));
-    long long T_start[MAX_CTX];
-    int ren_start[MAX_CTX];
-    for (int s = 0; s < nctx; s++) {
-        T_start[s] = ds[s]->h_ctl->T;
-        ren_start[s] = ds[s]->h_ctl->renorm_count;
-        if (renorms_out) renorms_out[s] = 0;
-    }
-    constexpr int BATCH_STAGES = 8192;
-    const int fused_total = nbits / FK * FK;
-    int pos = 0;
-    bool lockstep = true;
-    while (lockstep && pos < fused_total) {
-        const int end = std::min(fused_total, pos + BATCH_STAGES);
-        const int npasses = (end - pos) / FK;
-        MultiArgs m;
-        m.nctx = nctx;
-        m.npasses = npasses;
-        for (int s = 0; s < nctx; s++) {
-            Decoder *d = ds[s];
-            if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
-            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->optab, d->len,
-                                   pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
-        }
-        if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
-        CU(launch_persist(m, st));
-        if (d0->time_kernels) CU(cudaEventRecord(d0->kev1, st));
-        d0->launches += 2 * nctx + 1;
-        for (int s = 0; s < nctx; s++) {
-            Decoder *d = ds[s];
-            CU(cudaMemcpyAsync(d->h_ctl, d->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, st));
-        }
-        CU(cudaStreamSynchronize(st));
-        if (d0->time_kernels) {
-            float ms = 0;
-            CU(cudaEventElapsedTime(&ms, d0->kev0, d0->kev1));
-            d0->acs_ms += ms;
-            d0->acs_launches_timed += 2 * nctx + 1;
-            d0->acs_passes_timed += (unsigned long long)npasses * nctx;
-        }
-        for (int s = 0; s < nctx; s++) {
-            if (ds[s]->h_ctl->error) { set_err("device control block reports invariant violation %d", ds[s]->h_ctl->error); return -1; }
-            if (ds[s]->h_ctl->T - T_start[s] < end) lockstep = false;      // a decoder declined a pass: finish everyone one by one
-        }
-        pos = end;
-    }
-    // remainders (and the rare decoder that left lockstep) go through the single-decoder path, which resumes at ctl->pos
-    for (int s = 0; s < nctx; s++) {
-        Decoder *d = ds[s];
-        const int done = (int)(d->h_ctl->T - T_start[s]), ren = d->h_ctl->renorm_count - ren_start[s];
-        int r = 0;
-        if (done < nbits) {
-            // hand the decoder's own stream the rest; everything so far ran on d0's stream and is complete
-            r = update_core(d, dev_syms[s] + 2 * (size_t)done, nbits - done);
-            if (r < 0) return -1;
-        }
-        if (renorms_out) renorms_out[s] = ren + r;
-    }
-    return 0;
+    return multi_update_core(ds, dev_syms, nctx, nbits, renorms_out);
 }
 
 int v224x_stream_decode_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out)
@@ -558,6 +691,33 @@ int v224x_stream_decode(void *p, const unsigned char *syms, int nbits, int delay
     CU(cudaMemcpyAsync(bits_out, d->dout, (size_t)nbits, cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
     return r;
+}
+
+int v224x_stream_decode_seg_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out, int nseg, int conv,
+                                v224x_seg_report *rep)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits <= 0) return 0;
+    if (bind(d)) return -1;
+    return seg_core(d, dev_syms, nbits, delay, dev_bits_out, nseg, conv, rep) < 0 ? -1 : 0;
+}
+
+int v224x_stream_decode_seg(void *p, const unsigned char *syms, int nbits, int delay, unsigned char *bits_out, int nseg, int conv,
+                            v224x_seg_report *rep)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nbits <= 0) return 0;
+    if (bind(d)) return -1;
+    if (grow((void **)&d->dsyms, &d->dsyms_cap, 2 * (size_t)nbits)) return -1;
+    if (grow((void **)&d->dout, &d->dout_cap, (size_t)nbits)) return -1;
+    CU(cudaMemcpyAsync(d->dsyms, syms, 2 * (size_t)nbits, cudaMemcpyHostToDevice, d->stream));
+    uint8_t *dsyms = d->dsyms, *dout = d->dout;          // the handle's body may be exchanged with the last segment's decoder
+    if (seg_core(d, dsyms, nbits, delay, dout, nseg, conv, rep) < 0) return -1;
+    CU(cudaMemcpyAsync(bits_out, dout, (size_t)nbits, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
 }
 
 void *v224x_dev_alloc(void *p, size_t bytes)

@@ -263,6 +263,62 @@ def test_long_delay_stream_and_checkpoint_window():
                 assert crc(o.get_row(row)) == crc(d.get_row(row)), k
 
 
+@pytest.mark.parametrize("nseg,style,ebn0", [(2, "telemetry", 3.0), (3, "vtest", 1.0), (4, "telemetry", 2.0)])
+def test_lockstep_segmented_stream_equals_sequential(nseg, style, ebn0):
+    """v224x_stream_decode_seg: nseg decoders in lockstep over contiguous segments, every hand-over verified on the
+    device (metric vectors equal up to a constant) -> output identical to the sequential block decode."""
+    n, delay, conv = 70001, 200, 1024
+    if style == "telemetry":
+        bits, syms = S.telemetry_stream(n, ebn0, seed=90 + nseg)
+    else:
+        rng = np.random.default_rng(90 + nseg)
+        bits = rng.integers(0, 2, n, dtype=np.uint8)
+        sym01, _ = S.encode_bits(bits, 0)
+        syms = S.awgn_vtest(sym01, ebn0, rng)
+    with v224.Viterbi224(delay + 4096) as d:
+        d.init(0)
+        want, _ = d.stream_decode(syms, delay)
+    with v224.Viterbi224(delay + 4096) as d:
+        d.init(0)
+        got, rep = d.stream_decode_seg(syms, delay, nseg, conv)
+        assert rep["segments"] == nseg and rep["verified"] == nseg - 1 and rep["redone"] == 0 and rep["worst_spread"] == 0, rep
+        assert rep["warm"] == delay + conv and rep["extra_stages"] == (nseg - 1) * (delay + conv)
+        assert np.array_equal(got, want)
+        # the handle continues the stream exactly: 40 more stages, per-bit ABI, against a sequential decoder
+        tail = syms[:80]
+        a = [(d.update_blk(tail[2 * i: 2 * i + 2], 1), d.decodebit(delay, 0))[1] for i in range(40)]
+    with v224.Viterbi224(delay + 4096) as d:
+        d.init(0)
+        d.stream_decode(syms, delay)
+        b = [(d.update_blk(tail[2 * i: 2 * i + 2], 1), d.decodebit(delay, 0))[1] for i in range(40)]
+    assert a == b
+    lag = delay + 22
+    if ebn0 >= 3.0:
+        assert np.array_equal(got[lag:], bits[: n - lag])
+
+
+def test_segmented_stream_failed_handover_is_redone_exactly():
+    """conv = 0 puts the hand-over check at the very start of the later decoders (uniform metrics against the
+    true ones): it must fail, and the call must fall back to the sequential decode -- still bit-exact."""
+    n, delay = 30000, 96
+    bits, syms = S.telemetry_stream(n, 3.0, seed=97)
+    with v224.Viterbi224(delay + 2048) as d:
+        d.init(0)
+        want, _ = d.stream_decode(syms, delay)
+    with v224.Viterbi224(delay + 2048) as d:
+        d.init(0)
+        got, rep = d.stream_decode_seg(syms, delay, 3, 0)
+        assert rep["segments"] == 3 and rep["verified"] == 0 and rep["redone"] == 2 and rep["worst_spread"] > 0, rep
+        assert np.array_equal(got, want)
+        short, rep2 = d.stream_decode_seg(syms[:2 * 3000], delay, 4, 1024)       # too short for segments
+        assert rep2["segments"] == 1
+    with v224.Viterbi224(delay + 2048) as d:
+        d.init(0)
+        d.stream_decode(syms, delay)
+        want2, _ = d.stream_decode(syms[:2 * 3000], delay)
+    assert np.array_equal(short, want2)
+
+
 def test_time_segmented_decode_matches_single_pass():
     """Multi-GPU partitioning run on one GPU: segments with warm-up reproduce the single-pass output
     wherever survivors merged inside the warm-up; residual differences are counted (north_star)."""
