@@ -18,6 +18,7 @@
 #include "v224_common.cuh"
 #include "v224_fused_core.cuh"
 #include "v224_kernels.h"
+#include <cuda.h>          // CUtensorMap and the cuTensorMapEncodeTiled prototype only; the entry point is fetched at run time
 
 namespace v224 {
 
@@ -103,9 +104,29 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+    // the third operand is the suspend-time hint: the warp sleeps in hardware until the phase completes (or that long)
+    // instead of spinning through the issue slots the compute warps need
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_addr(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// bulk asynchronous copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// one tile = one 2-D tensor copy: box 64 columns x 256 rows at column x0 (TMA engine; bytes counted on the mbarrier)
+__device__ __forceinline__ void tma_load_tile(void *smem_dst, const void *tmap, int x0, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_addr(smem_dst)), "l"(tmap), "r"(x0), "r"(0), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()        { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem()   { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bar_compute()     // the compute warps' own barrier (the protocol warp never joins)
 {
     asm volatile("bar.sync 1, %0;" ::"n"(FUSED_THREADS) : "memory");
@@ -126,12 +147,22 @@ struct TileInfo {
     int n, s;            // pass and decoder (protocol warp's own bookkeeping)
     int pad[2];
 };
-struct __align__(16) FusedSmem {
-    uint32_t tile[XCHG_BUFS][256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 (32 KiB each): round-1 -> round-2 exchange
-    uint32_t tab[2][PASSTAB_WORDS];                          // operand table + ring rows of the tile's pass
-    TileInfo info[2];
+// Tile k of a CTA uses bookkeeping slot k % NSLOT (info, pass table, full/done barriers) and data buffer k % XCHG_BUFS.
+// A data buffer is free again as soon as the tile's round-2 reads are over (`freeb`), long before its stores are out
+// (`done`), so the protocol warp can have the input of tile k+2 in flight while tile k is still in its second round.
+// NSLOT = 2 (one tile of run-ahead) is the measured optimum: with 3-4 slots the protocol warps pre-claim most of
+// the tiles that are in flight and the dynamic queue stops balancing (3 decoders: 9.2 us per pass at 2 slots, 10.0 at 4).
+#ifndef V224_NSLOT
+#define V224_NSLOT 2
+#endif
+constexpr int NSLOT = V224_NSLOT;
+struct __align__(128) FusedSmem {
+    uint32_t tile[XCHG_BUFS][256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 (32 KiB each): tile input (bulk mode) and round-1 -> round-2 exchange
+    uint32_t tab[NSLOT][PASSTAB_WORDS];                      // operand table + ring rows of the tile's pass
+    TileInfo info[NSLOT];
     uint32_t s0[FK + 4];                                     // state-0 metric after each stage (meaningful in tile 0 only)
-    uint64_t full[2], done[2];                               // mbarriers: tile handed over / tile's stores issued
+    uint64_t full[NSLOT], done[NSLOT];                       // mbarriers: tile handed over (and its input landed) / tile's stores issued
+    uint64_t freeb[2];                                       // mbarriers: the data buffer's last reader is through
 };
 
 // Per-pass tables of a whole launch: the operand table from the pass's 8 symbol pairs, and the ring row of each
@@ -183,7 +214,7 @@ __device__ __forceinline__ uint32_t xchg_index(uint32_t m, uint32_t g)
 // Tile `tau` = columns [64 tau, 64 tau + 64) of all 256 rows.  Metrics are read through L2 only (another SM wrote
 // them, possibly within this launch).  `xbuf` = this tile's exchange buffer.
 template <bool CAREFUL>
-__device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, int trace_n)
+__device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, uint64_t *freeb, int trace_n)
 {
     const uint32_t tid = threadIdx.x, tau = ti.tau, sub = ti.sub2;
     PassStats *st = ti.st;
@@ -194,15 +225,30 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
         uint32_t thr, g;
         round1_map(tid, thr, g);
         const uint32_t G = tau * FUSED_COLGROUPS + g;              // global column group: columns COLW*G ..
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(ti.oldm) + ((size_t)thr * 32768 + (size_t)G * COLW) * 2;
+        if (BULK_LOAD) {
+            // the protocol warp's bulk copies put the tile into this buffer (row m at 128 m bytes) before the hand-over
 #pragma unroll
-        for (int mh = 0; mh < 16; mh++) {
-            if (NQ == 4) {
-                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)mh * 16 * 65536));
-                A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
-            } else {
-                const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(src + (size_t)mh * 16 * 65536));
-                A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+            for (int mh = 0; mh < 16; mh++) {
+                const uint32_t e = (mh * 16 + thr) * FUSED_COLGROUPS + g;
+                if (NQ == 4) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(xbuf)[e];
+                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
+                } else {
+                    const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
+                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+                }
+            }
+        } else {
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(ti.oldm) + ((size_t)thr * 32768 + (size_t)G * COLW) * 2;
+#pragma unroll
+            for (int mh = 0; mh < 16; mh++) {
+                if (NQ == 4) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)mh * 16 * 65536));
+                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
+                } else {
+                    const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(src + (size_t)mh * 16 * 65536));
+                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+                }
             }
         }
         TRACE(trace_n, tau, 2);
@@ -212,7 +258,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
         fused_stage<3, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
         fused_stage<4, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
         // ---- exchange: rows m = mh*16 + ml ----
-        if (XCHG_BUFS == 1) bar_compute();                         // the previous tile's round-2 reads are over
+        // The exchange happens in place: a thread writes exactly the rows it read (the swizzle only moves elements
+        // between lanes of its own warp).  With a single buffer the previous tile's round-2 reads must be over.
+        if (BULK_LOAD) __syncwarp();
+        else if (XCHG_BUFS == 1) bar_compute();
 #pragma unroll
         for (int mh = 0; mh < 16; mh++) {
             const uint32_t e = xchg_index(mh * 16 + thr, g);
@@ -236,6 +285,12 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
                 A[ml][0] = v.x; A[ml][1] = v.y;
             }
+        }
+        if (BULK_LOAD) {
+            // this warp is through with the data buffer: the protocol warp may bulk-copy the tile after next into it
+            fence_proxy_async_smem();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(freeb);
         }
         TRACE(trace_n, tau, 3);
         const uint32_t pbase = (thr << 19) | (G << COLW_LOG2);
@@ -388,38 +443,59 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
     const unsigned lane = threadIdx.x & 31;
     unsigned *queue = &m.ctx[0].ctl->pc.next_item;
     const unsigned per_pass = (unsigned)m.nctx * FUSED_TILES;
-    unsigned k_prep = 0, k_sig = 0;        // tiles prepared / published so far
+    unsigned k_prep = 0, k_done = 0;       // tiles handed over / tiles whose stores are issued (their slot is free again)
     bool have_item = false, exiting = false;
     unsigned item = 0, spins = 0;
     int n = 0;
     unsigned s = 0, tau = 0;
+    // a finished tile that still has to be published (kept in registers so that its slot can be refilled first)
+    bool pend = false;
+    int p_go = 0, p_n = 0, p_s = 0;
+    unsigned p_tau = 0;
+    // A finished tile is published before the next one is handed over.  The other order (claim, poll and bulk copy
+    // first, so that the input lands earlier) was measured slower at every decoder count (3 decoders: 10.2 against
+    // 9.2 us per pass): the passes' completion counters are what everybody else is waiting for.
+#ifndef V224_PREPARE_FIRST
+#define V224_PREPARE_FIRST 0
+#endif
+    const bool prepare_first = V224_PREPARE_FIRST && m.nctx > 1;
 
     for (;;) {
         bool progress = false;
-        // ---- publish finished tiles ----
-        // Nothing else to do (next tile already handed over, or no more work): sleep on the mbarrier instead of polling it.
-        if (k_sig < k_prep && (k_prep - k_sig == 2 || exiting)) mbar_wait(&sm.done[k_sig & 1], (k_sig >> 1) & 1);
-        if (k_sig < k_prep && mbar_test(&sm.done[k_sig & 1], (k_sig >> 1) & 1)) {
-            const TileInfo &ti = sm.info[k_sig & 1];
-            if (ti.go > 0 && lane == 0) {
-                Ctl *c = m.ctx[ti.s].ctl;
-                PassSlot &sl = c->pc.slot[ti.n % PSLOTS];
+        // ---- A. has a tile finished? ----
+        if (!pend && k_done < k_prep) {
+            const unsigned i = k_done % NSLOT, par = (k_done / NSLOT) & 1;
+            // Nothing else to do (every slot handed over, or no more work): sleep on the mbarrier instead of polling it.
+            if (k_prep - k_done == NSLOT || exiting) mbar_wait(&sm.done[i], par);
+            if (mbar_test(&sm.done[i], par)) {
+                const TileInfo &ti = sm.info[i];
+                p_go = ti.go; p_n = ti.n; p_s = ti.s; p_tau = ti.tau;
+                pend = true;
+                k_done++;
+                progress = true;
+            }
+        }
+        // ---- C. publish it: release-add on the pass's done word; the pass's last tile runs the resolver ----
+        if (pend && (!prepare_first || exiting || k_prep - k_done >= NSLOT)) {
+            if (p_go > 0 && lane == 0) {
+                Ctl *c = m.ctx[p_s].ctl;
+                PassSlot &sl = c->pc.slot[p_n % PSLOTS];
                 // release: the compute warps' stores (ordered before this thread by the mbarrier) become visible GPU-wide
                 // before the tile counts as done
-                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(ti.tau % TILE_CLASSES));
-                TRACE(ti.n, ti.tau, 6);
-                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, ti.n);
-                TRACE(ti.n, ti.tau, 7);
+                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(p_tau % TILE_CLASSES));
+                TRACE(p_n, p_tau, 6);
+                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, p_n);
+                TRACE(p_n, p_tau, 7);
             }
             __syncwarp();
-            k_sig++;
-            progress = true;
+            pend = false;
         }
         if (exiting) {
-            if (k_sig == k_prep) break;
-        } else if (k_prep - k_sig < 2) {
-            // ---- prepare the next tile ----
-            const unsigned b = k_prep & 1;
+            if (!pend && k_done == k_prep) break;
+        } else if (k_prep - k_done < NSLOT &&
+                   (!BULK_LOAD || k_prep < 2 || mbar_test(&sm.freeb[k_prep & 1], ((k_prep - 2) >> 1) & 1))) {
+            // ---- prepare the next tile: bookkeeping slot b, data buffer k_prep & 1 (free: tile k_prep - 2 has read it) ----
+            const unsigned b = k_prep % NSLOT;
             if (!have_item) {
                 if (lane == 0) item = atomicAdd(queue, 1u);
                 item = __shfl_sync(0xffffffffu, item, 0);
@@ -463,6 +539,7 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
                 }
                 if (stopped || ready) {
                     fence_acq_rel();                           // acquire: the producers' metric stores, the pass parameters
+                    if (BULK_LOAD) fence_proxy_async();        // ... which the bulk-copy engine (async proxy) is about to read
                     if (lane == 0) {
                         TileInfo &ti = sm.info[b];
                         const int cur = (a.cur0 + n) % NBUF;    // buffers advance by one per resolved pass
@@ -479,25 +556,49 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
                         TRACE(n, tau, 1);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full[b]);
+                    if (BULK_LOAD && !stopped) {
+                        // the tile (256 rows x 128 bytes, rows 64 KiB apart) -> shared memory in one tensor copy; the hand-over
+                        // completes when the bytes have landed
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&sm.full[b], 256u * 128u);
+                            const int cur = (a.cur0 + n) % NBUF;
+                            tma_load_tile(sm.tile[k_prep & 1], reinterpret_cast<const uint8_t *>(a.tmaps) + (size_t)cur * TMAP_BYTES, (int)(tau * FUSED_TILE_COLS), &sm.full[b]);
+                        }
+                    } else if (lane == 0) {
+                        mbar_arrive(&sm.full[b]);
+                    }
                     k_prep++;
                     have_item = false;
                     progress = true;
                 }
             }
         }
-        if (!progress) __nanosleep(k_sig < k_prep ? 40 : 100);    // a running tile to watch for / only dependencies to wait for
+        // ---- C'. throughput mode: the finished tile is published after the hand-over attempt ----
+        if (pend) {
+            if (p_go > 0 && lane == 0) {
+                Ctl *c = m.ctx[p_s].ctl;
+                PassSlot &sl = c->pc.slot[p_n % PSLOTS];
+                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(p_tau % TILE_CLASSES));
+                TRACE(p_n, p_tau, 6);
+                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, p_n);
+                TRACE(p_n, p_tau, 7);
+            }
+            __syncwarp();
+            pend = false;
+            progress = true;
+        }
+        if (!progress) __nanosleep(k_done < k_prep ? 40 : 100);   // a running tile to watch for / only dependencies to wait for
     }
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_persist(MultiArgs m)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1);
-        mbar_init(&sm.done[0], FUSED_THREADS / 32); mbar_init(&sm.done[1], FUSED_THREADS / 32);
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.full[i], 1); mbar_init(&sm.done[i], FUSED_THREADS / 32); }
+        mbar_init(&sm.freeb[0], FUSED_THREADS / 32); mbar_init(&sm.freeb[1], FUSED_THREADS / 32);
     }
     __syncthreads();
     if (tid >= FUSED_THREADS) {
@@ -505,15 +606,18 @@ __global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_p
         return;
     }
     for (unsigned k = 0;; k++) {
-        const unsigned b = k & 1;
-        mbar_wait(&sm.full[b], (k >> 1) & 1);
+        const unsigned b = k % NSLOT;
+        mbar_wait(&sm.full[b], (k / NSLOT) & 1);
         const TileInfo &ti = sm.info[b];
         const int go = ti.go;
         if (go < 0) break;
         if (go > 0) {
-            uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? b : 0];
-            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, ti.n);
-            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, ti.n);
+            uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? (k & 1) : 0];
+            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
+            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
+        } else if (BULK_LOAD) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.freeb[k & 1]);     // a skipped tile still hands its buffer on
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&sm.done[b]);      // this warp's stores of tile k are issued; it is done with slot b
@@ -524,6 +628,34 @@ __global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_p
 // launch
 // ------------------------------------------------------------------------------------------
 size_t passtab_bytes(int npasses) { return (size_t)npasses * PASSTAB_WORDS * sizeof(uint32_t); }
+
+cudaError_t build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) { if (why) *why = "cuTensorMapEncodeTiled not available"; return e != cudaSuccess ? e : cudaErrorNotSupported; }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    static_assert(sizeof(CUtensorMap) == TMAP_BYTES, "tensor map size");
+    alignas(64) CUtensorMap maps[NBUF];
+    for (int i = 0; i < NBUF; i++) {
+        const cuuint64_t dims[2] = {32768, 256};                 // innermost first: columns j, rows m
+        const cuuint64_t strides[1] = {65536};                   // bytes between rows
+        const cuuint32_t box[2] = {FUSED_TILE_COLS, 256};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, metrics[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { if (why) *why = "cuTensorMapEncodeTiled failed"; return cudaErrorInvalidValue; }
+    }
+    cudaError_t e = cudaMemcpyAsync(dev_out, maps, sizeof maps, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);                            // `maps` lives on this stack frame
+}
 
 // One persistent launch over m.nctx decoders x m.npasses passes (+ one table build and one begin kernel per decoder).
 cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)

@@ -56,6 +56,13 @@ constexpr int FUSED_CTAS_PER_SM = V224_CTAS_PER_SM;
 #define V224_XCHG_BUFS (V224_CTAS_PER_SM <= 3 ? 2 : 1)
 #endif
 constexpr int XCHG_BUFS = V224_XCHG_BUFS;
+// The protocol warp prefetches a tile's input into its exchange buffer with bulk asynchronous copies (TMA engine)
+// while the compute warps still work on the previous tile; needs the double buffer.
+#ifndef V224_BULK_LOAD
+#define V224_BULK_LOAD (V224_XCHG_BUFS == 2)
+#endif
+constexpr bool BULK_LOAD = V224_BULK_LOAD;
+static_assert(!BULK_LOAD || XCHG_BUFS == 2, "bulk prefetch needs the double exchange buffer");
 constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512 tiles per pass
 constexpr int TILE_CLASSES    = 128 / FUSED_TILE_COLS; // tile t of pass n+1 reads the tiles == (t >> 8) mod TILE_CLASSES of pass n
 

@@ -94,7 +94,13 @@ __host__ __device__ constexpr uint32_t slotmask(uint32_t poly, int t)
 template <int T> V224_HD uint32_t slot_label(uint32_t p)
 {
     constexpr uint32_t m1 = slotmask(POLY1, T), m2 = slotmask(POLY2, T);
-    return (f_popc(p & m1) & 1u) | ((f_popc(p & m2) & 1u) << 1);
+    // POLY1 ^ POLY2 is a single register bit (code.h:59-60), so the two masks differ in at most one slot bit:
+    // one population count serves both parities
+    constexpr uint32_t dm = m1 ^ m2;
+    static_assert((dm & (dm - 1)) == 0, "the polynomials differ in one bit");
+    const uint32_t e1 = f_popc(p & m1) & 1u;
+    const uint32_t e2 = dm ? (e1 ^ ((p & dm) ? 1u : 0u)) : e1;
+    return e1 | (e2 << 1);
 }
 constexpr uint32_t FLIP_LABEL = (uint32_t)G1FLIP | ((uint32_t)G2FLIP << 1);
 

@@ -10,6 +10,7 @@ struct PersistArgs {
     uint32_t *ring;
     uint8_t *row_fmt;
     const uint8_t *syms;     // symbols of the running update call; this launch starts at stage pos0
+    const void *tmaps;       // device array of NBUF tensor maps (128 bytes each): metrics[i] as a [256][32768] uint16 tensor, box 256 x 64
     uint32_t *passtab;       // npasses x PASSTAB_WORDS words (operand table + ring rows), filled by k_build_passtab at launch
     int len;
     int pos0;                // stages of this call already done when the launch starts
@@ -50,6 +51,9 @@ struct TraceArgs {
 cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, int start_value, cudaStream_t st);
 cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st);
 size_t passtab_bytes(int npasses);
+// tensor maps of a decoder's NBUF metric buffers ([256 rows][32768 columns] of uint16, box = one tile) into dev_out (NBUF x 128 bytes)
+cudaError_t build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why);
+constexpr size_t TMAP_BYTES = 128;
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st);
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);

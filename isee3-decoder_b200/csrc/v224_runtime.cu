@@ -95,6 +95,7 @@ struct Decoder {
     Ctl *ctl;
     Ctl *h_ctl;                 // pinned mirror, refreshed at the end of every update
     uint8_t *dsyms; size_t dsyms_cap;
+    void *tmaps;                            // NBUF tensor maps of the metric buffers (device memory)
     uint32_t *optab; size_t optab_cap;     // per-pass tables (operands + ring rows) of the running batch
     uint8_t *dout;  size_t dout_cap;       // chainback / stream output staging
     uint32_t *seg;  size_t seg_cap;        // chainback segment bookkeeping
@@ -159,7 +160,7 @@ void destroy(Decoder *d)
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
     for (int i = 0; i < NBUF; i++) cudaFree(d->metrics[i]);
     cudaFree(d->row_fmt); cudaFree(d->ctl);
-    cudaFree(d->optab);
+    cudaFree(d->optab); cudaFree(d->tmaps);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
     cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag); cudaFree(d->snap); cudaFree(d->d_segdiff);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
@@ -214,7 +215,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
                 MultiArgs m;
                 m.nctx = 1;
                 m.npasses = npasses;
-                m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->optab, d->len, p,
+                m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->tmaps, d->optab, d->len, p,
                                        (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
                 CU(launch_persist(m, d->stream));
                 p += npasses * FK;
@@ -281,7 +282,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         for (int s = 0; s < nctx; s++) {
             Decoder *d = ds[s];
             if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
-            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->optab, d->len,
+            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->tmaps, d->optab, d->len,
                                    pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
         }
         if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
@@ -355,6 +356,10 @@ void swap_bodies(Decoder *d, Decoder *o)
     *o = td;
     for (int i = 0; i < MAX_CTX - 1; i++) { d->aux[i] = td.aux[i]; o->aux[i] = nullptr; }
     d->d_segdiff = td.d_segdiff; o->d_segdiff = to.d_segdiff;
+    // streams and events stay with the handle too (a timer started on the handle must stop on the same events)
+    d->stream = td.stream; o->stream = to.stream;
+    d->ev0 = td.ev0; d->ev1 = td.ev1; d->kev0 = td.kev0; d->kev1 = td.kev1;
+    o->ev0 = to.ev0; o->ev1 = to.ev1; o->kev0 = to.kev0; o->kev1 = to.kev1;
     d->force_single = td.force_single; d->force_sat = td.force_sat; d->force_careful = td.force_careful;
     d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm;
     d->time_kernels = td.time_kernels; d->acs_ms = td.acs_ms; d->acs_launches_timed = td.acs_launches_timed;
@@ -492,6 +497,15 @@ void *create_viterbi224(int len)
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < NBUF; i++) ok = ok && cudaMalloc(&d->metrics[i], METRICBYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->tmaps, NBUF * TMAP_BYTES) == cudaSuccess;
+    if (ok) {
+        const char *why = nullptr;
+        if (build_metric_tensor_maps(d->metrics, d->tmaps, d->stream, &why) != cudaSuccess) {
+            set_err("create_viterbi224(%d): tensor maps: %s", len, why ? why : cudaGetErrorString(cudaGetLastError()));
+            destroy(d);
+            return nullptr;
+        }
+    }
     ok = ok && cudaMalloc(&d->row_fmt, (size_t)len) == cudaSuccess;
     ok = ok && cudaMalloc(&d->ctl, sizeof(Ctl)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->d_redo, sizeof(unsigned)) == cudaSuccess;
@@ -770,9 +784,9 @@ float v224x_timer_stop_ms(void *p)
 {
     Decoder *d = as_dec(p);
     if (!d || bind(d)) return -1.f;
-    if (cudaEventRecord(d->ev1, d->stream) != cudaSuccess || cudaEventSynchronize(d->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventRecord(d->ev1, d->stream) != cudaSuccess || cudaEventSynchronize(d->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     float ms = -1.f;
-    if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }   // do not leave the error for the next launch
     return ms;
 }
 int v224x_kernel_time_reset(void *p)

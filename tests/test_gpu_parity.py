@@ -297,6 +297,24 @@ def test_lockstep_segmented_stream_equals_sequential(nseg, style, ebn0):
         assert np.array_equal(got[lag:], bits[: n - lag])
 
 
+def test_segmented_stream_keeps_handle_identity():
+    """The handle's body is exchanged with the last segment's decoder; its stream, timer events and options stay:
+    a timer started before an odd number of segmented calls stops cleanly, and the next ABI call works."""
+    n, delay = 40000, 64
+    bits, syms = S.telemetry_stream(n, 4.0, seed=98)
+    with v224.Viterbi224(delay + 2048) as d:
+        d.set_option("chain_seg", 64)
+        d.init(0)
+        d.timer_start()
+        got, rep = d.stream_decode_seg(syms, delay, 3, 512)
+        ms = d.timer_stop_ms()
+        assert rep["segments"] == 3 and rep["redone"] == 0
+        assert ms > 0
+        assert d.init(0) == 0
+        again, _ = d.stream_decode(syms, delay)
+        assert np.array_equal(got, again)
+
+
 def test_segmented_stream_failed_handover_is_redone_exactly():
     """conv = 0 puts the hand-over check at the very start of the later decoders (uniform metrics against the
     true ones): it must fail, and the call must fall back to the sequential decode -- still bit-exact."""
