@@ -101,6 +101,7 @@ typedef struct {
     unsigned long long chainback_redo; /* speculative chainback segments that had to be redone  */
     long long          renormals;      /* the reference's `renormals` accumulator               */
     long long          stages;         /* trellis stages since the last init                    */
+    unsigned long long walk_steps;     /* dependent ring loads spent in decodebit(delay, state>=0) walks */
 } v224x_stats;
 int v224x_get_stats(void *p, v224x_stats *out);
 
@@ -115,7 +116,8 @@ int v224x_get_row(void *p, int row, uint32_t *host_out);
 /* Knobs: "force_single"=1 never fuse, "force_sat"=1 exact saturating single stages only,
  * "force_careful"=1 always record per-stage minima, "per_pass_launch"=1 one kernel launch per
  * 8-stage pass instead of the persistent multi-pass kernel, "chain_seg"/"chain_warm" chainback
- * segment length / warm-up depth. */
+ * segment length / warm-up depth, "no_walk_cache"=1 decodebit always walks all `delay` rows (default: it stops where the
+ * walk rejoins the previous call's path, same result). */
 int v224x_set_option(void *p, const char *key, long long value);
 
 #ifdef __cplusplus

@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_ulonglong), ("fused_passes", ctypes.c_ulonglong), ("careful_passes", ctypes.c_ulonglong),
                 ("single_stages", ctypes.c_ulonglong), ("sat_stages", ctypes.c_ulonglong), ("invalidated_passes", ctypes.c_ulonglong),
                 ("chainback_redo", ctypes.c_ulonglong),
-                ("renormals", ctypes.c_longlong), ("stages", ctypes.c_longlong)]
+                ("renormals", ctypes.c_longlong), ("stages", ctypes.c_longlong), ("walk_steps", ctypes.c_ulonglong)]
 
 
 class SegReport(ctypes.Structure):

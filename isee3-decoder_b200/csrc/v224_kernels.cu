@@ -263,6 +263,37 @@ __global__ void k_walk(TraceArgs a, long long dp, int delay, uint32_t endstate, 
     result[1] = word;
 }
 
+// Incremental form of the same walk for the per-bit streaming pattern of vdecode.c:145-152 (update(1) + decodebit(delay, 0)
+// after every stage): survivors merge, so the walk from the new ring head rejoins the previous call's path after a
+// few steps; from there on the states are the ones cached last time and the answer is looked up.  cache[t % len] = state
+// of the path at time t (after the row of stage t was applied) for the previous walk, which started at head prev_T.
+// T = stages appended so far; rows T-delay .. T-1 must still be in the ring (len > delay) and unchanged since.
+// The result is identical to k_walk's; only the number of dependent loads differs.
+__global__ void k_walk_incremental(TraceArgs a, long long T, long long prev_T, int delay, uint32_t endstate, uint32_t *cache,
+                                   unsigned long long *result, unsigned *steps_out)
+{
+    uint32_t st = endstate & STATEMASK;
+    int bit = -1;
+    unsigned steps = 0;
+    for (long long t = T - 1; t >= T - delay; t--) {
+        const long long row = ((t % a.len) + a.len) % a.len;
+        bit = (int)read_decision(a.ring, a.row_fmt, row, st);
+        st = ((uint32_t)bit << (K - 2)) | (st >> 1);
+        steps++;
+        const bool cached = t <= prev_T - 1 && t >= prev_T - delay && t > T - delay;
+        if (cached && cache[row] == st) {
+            // merged with the previous path: the state at time T - delay is the cached one
+            const long long r2 = (((T - delay) % a.len) + a.len) % a.len;
+            bit = (int)((cache[r2] >> (K - 2)) & 1u);
+            break;
+        }
+        cache[row] = st;
+    }
+    result[0] = (unsigned long long)(long long)bit;
+    result[1] = 0;
+    if (steps_out) atomicAdd(steps_out, steps);
+}
+
 // Batched streaming traceback: output i is what decodebit(delay, 0) returns right after stage
 // T_first + i has been appended (vdecode.c:145-152).  Rows older than the last init read as 0.
 __global__ void k_stream_trace(TraceArgs a, long long T_first, int nout, int delay, uint8_t *bits_out)
@@ -403,6 +434,12 @@ cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t en
                         unsigned long long *result, cudaStream_t st)
 {
     k_walk<<<1, 1, 0, st>>>(a, dp, delay, endstate, use_argmin, argmin_key, result);
+    return cudaGetLastError();
+}
+cudaError_t launch_walk_incremental(const TraceArgs &a, long long T, long long prev_T, int delay, uint32_t endstate, uint32_t *cache,
+                                    unsigned long long *result, unsigned *steps_out, cudaStream_t st)
+{
+    k_walk_incremental<<<1, 1, 0, st>>>(a, T, prev_T, delay, endstate, cache, result, steps_out);
     return cudaGetLastError();
 }
 cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st)

@@ -59,6 +59,8 @@ cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endsta
                              uint32_t *seg_final, unsigned *redo_count, cudaStream_t st);
 cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t endstate, int use_argmin, const unsigned long long *argmin_key,
                         unsigned long long *result, cudaStream_t st);
+cudaError_t launch_walk_incremental(const TraceArgs &a, long long T, long long prev_T, int delay, uint32_t endstate, uint32_t *cache,
+                                    unsigned long long *result, unsigned *steps_out, cudaStream_t st);
 cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st);
 cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st);
 cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st);

@@ -104,13 +104,19 @@ struct Decoder {
     unsigned *d_mnmx;
     unsigned long long *d_result, *h_result;   // walk results (pinned host copy)
     int *d_flag;
+    // per-bit streaming (vdecode.c:145-152): the previous decodebit walk, so that the next one stops where it rejoins it
+    uint32_t *walk_cache;      // [len] state of the cached path at stage t, at index t % len
+    long long cache_T;         // ring head (stages since init) of the cached walk
+    int cache_delay, cache_valid;
+    uint32_t cache_end;
+    unsigned *d_walk_steps;    // dependent loads spent in decodebit walks (test / tuning counter)
     // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
     struct Decoder *aux[MAX_CTX - 1];
     uint16_t *snap;
     int *d_segdiff;            // [2 * MAX_CTX]: min / max of the metric difference at each hand-over check
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm;
+    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     double acs_ms;
@@ -162,7 +168,7 @@ void destroy(Decoder *d)
     cudaFree(d->row_fmt); cudaFree(d->ctl);
     cudaFree(d->optab); cudaFree(d->tmaps);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
-    cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag); cudaFree(d->snap); cudaFree(d->d_segdiff);
+    cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag); cudaFree(d->snap); cudaFree(d->d_segdiff); cudaFree(d->walk_cache); cudaFree(d->d_walk_steps);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
     if (d->h_result) cudaFreeHost(d->h_result);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -179,6 +185,7 @@ int do_init(Decoder *d, int bias, int start_state)
 {
     if (bind(d)) return -1;
     const uint32_t ss = start_state < 0 ? 0u : ((uint32_t)start_state & STATEMASK);
+    d->cache_valid = 0;
     CU(launch_init(d->metrics[0], d->ctl, ss, bias, start_state < 0 ? -1 : 0, d->stream));
     d->launches++;
     if (sync_ctl(d)) return -1;
@@ -361,7 +368,7 @@ void swap_bodies(Decoder *d, Decoder *o)
     d->ev0 = td.ev0; d->ev1 = td.ev1; d->kev0 = td.kev0; d->kev1 = td.kev1;
     o->ev0 = to.ev0; o->ev1 = to.ev1; o->kev0 = to.kev0; o->kev1 = to.kev1;
     d->force_single = td.force_single; d->force_sat = td.force_sat; d->force_careful = td.force_careful;
-    d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm;
+    d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm; d->no_walk_cache = td.no_walk_cache;
     d->time_kernels = td.time_kernels; d->acs_ms = td.acs_ms; d->acs_launches_timed = td.acs_launches_timed;
     d->acs_passes_timed = td.acs_passes_timed; d->launches = td.launches;
     o->time_kernels = to.time_kernels; o->acs_ms = to.acs_ms; o->acs_launches_timed = to.acs_launches_timed;
@@ -590,12 +597,35 @@ static int walk(Decoder *d, int delay, int endstate)
     return 0;
 }
 
+// decodebit with a fixed end state: same result as walk(), but the walk stops where it rejoins the previous call's
+// path (cached on the device).  Needs the `delay` newest rows in the ring, i.e. delay < len (vdecode.c:94 allocates delay + 1).
+static int walk_incremental(Decoder *d, int delay, uint32_t endstate)
+{
+    if (bind(d)) return -1;
+    if (!d->walk_cache) {
+        CU(cudaMalloc(&d->walk_cache, (size_t)d->len * sizeof(uint32_t)));
+        CU(cudaMalloc(&d->d_walk_steps, sizeof(unsigned)));
+        CU(cudaMemsetAsync(d->d_walk_steps, 0, sizeof(unsigned), d->stream));
+    }
+    const long long T = d->h_ctl->T;
+    const bool inc = d->cache_valid && d->cache_delay == delay && d->cache_end == endstate && T > d->cache_T && T - d->cache_T < delay;
+    const long long prev_T = inc ? d->cache_T : T - 4ll * d->len - 4ll * delay;      // no overlap: a full walk that fills the cache
+    CU(launch_walk_incremental(trace_args(d), T, prev_T, delay, endstate, d->walk_cache, d->d_result, d->d_walk_steps, d->stream));
+    d->launches++;
+    CU(cudaMemcpyAsync(d->h_result, d->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    d->cache_valid = 1; d->cache_T = T; d->cache_delay = delay; d->cache_end = endstate;
+    return 0;
+}
+
 int decodebit_viterbi224(void *p, int delay, int endstate)
 {
     Decoder *d = as_dec(p);
     if (!d) return -1;
     if (delay <= 0) return -1;
-    if (walk(d, delay, endstate)) return -1;
+    if (endstate >= 0 && delay < d->len && !d->no_walk_cache) {
+        if (walk_incremental(d, delay, (uint32_t)endstate & STATEMASK)) return -1;
+    } else if (walk(d, delay, endstate)) return -1;
     return (int)(long long)d->h_result[0];
 }
 
@@ -833,6 +863,9 @@ int v224x_get_stats(void *p, v224x_stats *out)
     out->chainback_redo = redo;
     out->renormals = d->h_ctl->renormals;
     out->stages = d->h_ctl->T;
+    unsigned steps = 0;
+    if (d->d_walk_steps) CU(cudaMemcpy(&steps, d->d_walk_steps, sizeof steps, cudaMemcpyDeviceToHost));
+    out->walk_steps = steps;
     return 0;
 }
 
@@ -862,6 +895,7 @@ int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, l
 {
     Decoder *d = as_dec(p);
     if (!d || bind(d)) return -1;
+    d->cache_valid = 0;
     int16_t *tmp = nullptr;
     CU(cudaMalloc(&tmp, METRICBYTES));
     int rc = 0;
@@ -901,6 +935,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "force_sat")) d->force_sat = (int)value;
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
+    else if (!strcmp(key, "no_walk_cache")) d->no_walk_cache = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }
