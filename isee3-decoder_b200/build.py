@@ -31,6 +31,25 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+HOST_PROGRAMS = {"vdecode_block": os.path.join(HERE, "host", "vdecode_block.cpp")}
+BIN = os.path.join(HERE, "bin")
+
+
+def build_host_programs(force=False):
+    """Host-side programs above the C ABI (plain C++, no CUDA): linked against the in-tree library, rpath relative."""
+    os.makedirs(BIN, exist_ok=True)
+    outs = []
+    for name, src in HOST_PROGRAMS.items():
+        exe = os.path.join(BIN, name)
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(LIB)):
+            cmd = ["g++", "-O2", "-Wall", "-std=c++17", "-o", exe, src, "-L" + HERE, "-lviterbi224_b200", "-Wl,-rpath,$ORIGIN/.."]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("host program build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        outs.append(exe)
+    return outs
+
+
 def build_library(force=False, verbose=False, out=None, extra_flags=()):
     """Compile the CUDA sources for sm_100a and link the shared library.  Returns its path.
     out / extra_flags: A/B builds of kernel-shape variants into another file (tools/build_variants.sh)."""
@@ -69,3 +88,4 @@ if __name__ == "__main__":
         print(build_library(out=os.path.abspath(sys.argv[2]), extra_flags=sys.argv[3:]))
     else:
         print(build_library(force=True, verbose=True))
+        print(build_host_programs(force=True))

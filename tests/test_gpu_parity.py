@@ -235,6 +235,36 @@ def test_stock_vdecode_on_gpu_library_and_block_mirror_agree_with_reference_outp
     assert np.array_equal(np.frombuffer(out.stdout, dtype=np.uint8), fx)
 
 
+def _status_lines(stderr_bytes):
+    """stderr without the program name (argv[0] differs between the two programs)."""
+    return [ln.split(b": ", 1)[1] for ln in stderr_bytes.splitlines() if b": " in ln]
+
+
+def test_native_block_driver_prints_what_stock_vdecode_prints():
+    """isee3-decoder_b200/bin/vdecode_block (C++ host program, one block call per 20,000 pairs, 3 decoders in lockstep)
+    against stock vdecode.c on the same library and against the fixture recorded from the unmodified reference:
+    stdout byte for byte, stderr (flip notices, re-encode symbol-error tally per status interval) line for line."""
+    blk = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    assert os.path.exists(blk), "vdecode_block not built (python __graft_entry__.py build)"
+    # (1) the reference's own output (fixture), small stream with a phase flip
+    bits, soft = S.telemetry_stream(3 * 1024, 6.0, seed=11, junk_symbols=101)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "vdecode_flip_seed11.npy"))
+    out = subprocess.run([blk, "-d", "64", "-q"], input=soft.tobytes(), capture_output=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert np.array_equal(np.frombuffer(out.stdout, dtype=np.uint8), fx)
+    # (2) a longer stream (several blocks, segmented decode inside, two flips: junk prefix + one dropped symbol mid-stream)
+    bits, soft = S.telemetry_stream(46 * 1024, 3.0, seed=12, junk_symbols=33)
+    soft = np.delete(soft, 61_007)
+    env = dict(os.environ, LANG="C")
+    args = ["-d", "200", "-i", "5000"]
+    a = subprocess.run([_bin("vdecode_b200")] + args, input=soft.tobytes(), capture_output=True, timeout=900, env=env)
+    b = subprocess.run([blk] + args + ["-B", "20000"], input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-300:], b.stderr[-300:])
+    assert a.stdout == b.stdout and len(a.stdout) > 46_000
+    la, lb = _status_lines(a.stderr), _status_lines(b.stderr)
+    assert la == lb and sum(b"flipping phase" in x for x in la) >= 2 and sum(b"symerrs" in x for x in la) >= 9, la
+
+
 # ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs)
 # ---------------------------------------------------------------------------------------------
