@@ -152,6 +152,13 @@ struct TileInfo {
 // (`done`), so the protocol warp can have the input of tile k+2 in flight while tile k is still in its second round.
 // NSLOT = 2 (one tile of run-ahead) is the measured optimum: with 3-4 slots the protocol warps pre-claim most of
 // the tiles that are in flight and the dynamic queue stops balancing (3 decoders: 9.2 us per pass at 2 slots, 10.0 at 4).
+// CLAIM_LATE (off): claim the next tile only when the running one has finished its second-round reads (about 60 % into
+// the tile) instead of at its start, to keep the window of committed queue items short.  Measured slower (3 decoders:
+// 9.96 against 9.29 us per pass): the protocol's round trips no longer fit behind the rest of the tile.
+#ifndef V224_CLAIM_LATE
+#define V224_CLAIM_LATE 0
+#endif
+constexpr bool CLAIM_LATE = V224_CLAIM_LATE;
 #ifndef V224_NSLOT
 #define V224_NSLOT 2
 #endif
@@ -286,9 +293,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 A[ml][0] = v.x; A[ml][1] = v.y;
             }
         }
-        if (BULK_LOAD) {
+        {
             // this warp is through with the data buffer: the protocol warp may bulk-copy the tile after next into it
-            fence_proxy_async_smem();
+            // (and, with CLAIM_LATE, only now claims the next tile)
+            if (BULK_LOAD) fence_proxy_async_smem();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(freeb);
         }
@@ -493,7 +501,9 @@ __device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
         if (exiting) {
             if (!pend && k_done == k_prep) break;
         } else if (k_prep - k_done < NSLOT &&
-                   (!BULK_LOAD || k_prep < 2 || mbar_test(&sm.freeb[k_prep & 1], ((k_prep - 2) >> 1) & 1))) {
+                   (!BULK_LOAD || k_prep < 2 || mbar_test(&sm.freeb[k_prep & 1], ((k_prep - 2) >> 1) & 1)) &&
+                   (!CLAIM_LATE || have_item || k_prep < 1 || k_done == k_prep ||
+                    mbar_test(&sm.freeb[(k_prep - 1) & 1], ((k_prep - 1) >> 1) & 1))) {
             // ---- prepare the next tile: bookkeeping slot b, data buffer k_prep & 1 (free: tile k_prep - 2 has read it) ----
             const unsigned b = k_prep % NSLOT;
             if (!have_item) {
@@ -615,7 +625,7 @@ __global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_p
             uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? (k & 1) : 0];
             if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
             else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
-        } else if (BULK_LOAD) {
+        } else {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.freeb[k & 1]);     // a skipped tile still hands its buffer on
         }
