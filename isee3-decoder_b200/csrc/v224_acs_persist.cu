@@ -23,17 +23,20 @@
 namespace v224 {
 
 #ifdef V224_TRACE
-__device__ unsigned long long g_trace[64 * 1024 * 8];      // [pass < 64][tile][event]
-__device__ unsigned g_smid[64 * 1024];
+// per (pass < 64, decoder < 4, tile < 512): 8 event timestamps (globaltimer ns) + the SM the tile ran on
+__device__ unsigned long long g_trace[64 * 4 * 512 * 8];
+__device__ unsigned g_smid[64 * 4 * 512];
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define TRACE(n, tau, ev) do { if ((threadIdx.x & 31) == 0 && (n) < 64) { g_trace[((n) * 1024 + (tau)) * 8 + (ev)] = gtime(); if ((ev) == 1) { unsigned sm_; asm volatile("mov.u32 %0, %smid;" : "=r"(sm_)); g_smid[(n) * 1024 + (tau)] = sm_; } } } while (0)
+#define TRACE(key, tau, ev) do { if ((threadIdx.x & 31) == 0 && (key) >= 0 && (key) < 256) { g_trace[(((size_t)(key)) * 512 + (tau)) * 8 + (ev)] = gtime(); if ((ev) == 1) { unsigned sm_; asm volatile("mov.u32 %0, %smid;" : "=r"(sm_)); g_smid[(size_t)(key) * 512 + (tau)] = sm_ | (blockIdx.x << 16); } } } while (0)
+#define TKEY(n, s) ((n) < 64 ? (n) * 4 + (int)(s) : -1)
 #else
-#define TRACE(n, tau, ev) do { } while (0)
+#define TRACE(key, tau, ev) do { } while (0)
+#define TKEY(n, s) 0
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -152,23 +155,18 @@ struct TileInfo {
 // (`done`), so the protocol warp can have the input of tile k+2 in flight while tile k is still in its second round.
 // NSLOT = 2 (one tile of run-ahead) is the measured optimum: with 3-4 slots the protocol warps pre-claim most of
 // the tiles that are in flight and the dynamic queue stops balancing (3 decoders: 9.2 us per pass at 2 slots, 10.0 at 4).
-// CLAIM_LATE (off): claim the next tile only when the running one has finished its second-round reads (about 60 % into
-// the tile) instead of at its start, to keep the window of committed queue items short.  Measured slower (3 decoders:
-// 9.96 against 9.29 us per pass): the protocol's round trips no longer fit behind the rest of the tile.
-#ifndef V224_CLAIM_LATE
-#define V224_CLAIM_LATE 0
-#endif
-constexpr bool CLAIM_LATE = V224_CLAIM_LATE;
 #ifndef V224_NSLOT
 #define V224_NSLOT 2
 #endif
 constexpr int NSLOT = V224_NSLOT;
+constexpr int CTA_THREADS = FUSED_THREADS + 64;              // compute warps + producer warp + retirer warp
 struct __align__(128) FusedSmem {
     uint32_t tile[XCHG_BUFS][256 * FUSED_TILE_COLS / 2];   // 256 rows x 64 columns of uint16 (32 KiB each): tile input (bulk mode) and round-1 -> round-2 exchange
     uint32_t tab[NSLOT][PASSTAB_WORDS];                      // operand table + ring rows of the tile's pass
     TileInfo info[NSLOT];
     uint32_t s0[FK + 4];                                     // state-0 metric after each stage (meaningful in tile 0 only)
     uint64_t full[NSLOT], done[NSLOT];                       // mbarriers: tile handed over (and its input landed) / tile's stores issued
+    uint64_t slotfree[NSLOT];                                // mbarriers: the tile is retired from its bookkeeping slot
     uint64_t freeb[2];                                       // mbarriers: the data buffer's last reader is through
 };
 
@@ -294,8 +292,7 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             }
         }
         {
-            // this warp is through with the data buffer: the protocol warp may bulk-copy the tile after next into it
-            // (and, with CLAIM_LATE, only now claims the next tile)
+            // this warp is through with the data buffer: the producer warp may bulk-copy the tile after next into it
             if (BULK_LOAD) fence_proxy_async_smem();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(freeb);
@@ -440,179 +437,141 @@ __device__ void resolve_persist(Ctl *c, int n)
     st_release(&pc.resolved_upto, (unsigned)(n + 1));
 }
 
-// The protocol warp's loop.  Two tile slots (b = k & 1): while the compute warps run tile k, tile k+1 is prepared.
-//   prepare(k): claim an item, fetch its pass table, wait for pass parameters + dependencies, publish info[b], arrive full[b]
-//   signal(k) : once done[b] completes (every compute warp issued tile k's stores): release-add the pass's done word,
-//               resolve the pass if this was its last tile; slot b is free again
-// Signalling never queues behind a dependency wait (a tile this CTA still has to publish may be exactly what its
-// next tile depends on), so the loop polls both.
-__device__ void protocol_warp(FusedSmem &sm, const MultiArgs &m)
+// Two protocol warps per CTA, so that the two chains of L2 round trips run side by side instead of one after the other
+// (measured: the serial chain -- publish, claim, poll, fence, tensor copy -- was longer than a tile's compute time and set
+// the CTA's cycle):
+//   producer: for tile k: wait until bookkeeping slot k % NSLOT is free, claim the next (pass, decoder, tile) item, poll its
+//             pass parameters and the previous pass's completion counters, fence, issue the tile's tensor copy, hand over.
+//   retirer : for tile k: wait until the compute warps have issued its stores, free the slot (the tile's identity moves into
+//             registers), publish the tile with one release-add on the pass's done word; the pass's last tile runs the resolver.
+// Neither waits for the other except through the slot hand-back, and a dependency wait of the producer never delays a
+// publication (a tile this CTA still has to publish may be exactly what its next tile depends on).
+__device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
 {
     const unsigned lane = threadIdx.x & 31;
     unsigned *queue = &m.ctx[0].ctl->pc.next_item;
     const unsigned per_pass = (unsigned)m.nctx * FUSED_TILES;
-    unsigned k_prep = 0, k_done = 0;       // tiles handed over / tiles whose stores are issued (their slot is free again)
-    bool have_item = false, exiting = false;
-    unsigned item = 0, spins = 0;
-    int n = 0;
-    unsigned s = 0, tau = 0;
-    // a finished tile that still has to be published (kept in registers so that its slot can be refilled first)
-    bool pend = false;
-    int p_go = 0, p_n = 0, p_s = 0;
-    unsigned p_tau = 0;
-    // A finished tile is published before the next one is handed over.  The other order (claim, poll and bulk copy
-    // first, so that the input lands earlier) was measured slower at every decoder count (3 decoders: 10.2 against
-    // 9.2 us per pass): the passes' completion counters are what everybody else is waiting for.
-#ifndef V224_PREPARE_FIRST
-#define V224_PREPARE_FIRST 0
-#endif
-    const bool prepare_first = V224_PREPARE_FIRST && m.nctx > 1;
-
-    for (;;) {
-        bool progress = false;
-        // ---- A. has a tile finished? ----
-        if (!pend && k_done < k_prep) {
-            const unsigned i = k_done % NSLOT, par = (k_done / NSLOT) & 1;
-            // Nothing else to do (every slot handed over, or no more work): sleep on the mbarrier instead of polling it.
-            if (k_prep - k_done == NSLOT || exiting) mbar_wait(&sm.done[i], par);
-            if (mbar_test(&sm.done[i], par)) {
-                const TileInfo &ti = sm.info[i];
-                p_go = ti.go; p_n = ti.n; p_s = ti.s; p_tau = ti.tau;
-                pend = true;
-                k_done++;
-                progress = true;
-            }
-        }
-        // ---- C. publish it: release-add on the pass's done word; the pass's last tile runs the resolver ----
-        if (pend && (!prepare_first || exiting || k_prep - k_done >= NSLOT)) {
-            if (p_go > 0 && lane == 0) {
-                Ctl *c = m.ctx[p_s].ctl;
-                PassSlot &sl = c->pc.slot[p_n % PSLOTS];
-                // release: the compute warps' stores (ordered before this thread by the mbarrier) become visible GPU-wide
-                // before the tile counts as done
-                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(p_tau % TILE_CLASSES));
-                TRACE(p_n, p_tau, 6);
-                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, p_n);
-                TRACE(p_n, p_tau, 7);
-            }
+    for (unsigned k = 0;; k++) {
+        const unsigned b = k % NSLOT;
+        if (k >= (unsigned)NSLOT) mbar_wait(&sm.slotfree[b], (k / NSLOT - 1) & 1);       // tile k - NSLOT is done with the slot
+        if (BULK_LOAD && k >= 2) mbar_wait(&sm.freeb[k & 1], ((k - 2) >> 1) & 1);      // tile k - 2 has read the data buffer
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(queue, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        const int n = (int)(item / per_pass);
+        const unsigned r = item % per_pass, w = r % FUSED_TILES, s = r / FUSED_TILES;
+        const uint32_t tau = (w % 256u) * TILE_CLASSES + w / 256u;          // a pass emits its tile classes in turn
+        if (n >= m.npasses) {
+            // no more work: tell the compute warps and the retirer
+            if (lane == 0) sm.info[b].go = -1;
             __syncwarp();
-            pend = false;
+            if (lane == 0) mbar_arrive(&sm.full[b]);
+            return;
         }
-        if (exiting) {
-            if (!pend && k_done == k_prep) break;
-        } else if (k_prep - k_done < NSLOT &&
-                   (!BULK_LOAD || k_prep < 2 || mbar_test(&sm.freeb[k_prep & 1], ((k_prep - 2) >> 1) & 1)) &&
-                   (!CLAIM_LATE || have_item || k_prep < 1 || k_done == k_prep ||
-                    mbar_test(&sm.freeb[(k_prep - 1) & 1], ((k_prep - 1) >> 1) & 1))) {
-            // ---- prepare the next tile: bookkeeping slot b, data buffer k_prep & 1 (free: tile k_prep - 2 has read it) ----
-            const unsigned b = k_prep % NSLOT;
-            if (!have_item) {
-                if (lane == 0) item = atomicAdd(queue, 1u);
-                item = __shfl_sync(0xffffffffu, item, 0);
-                n = (int)(item / per_pass);
-                const unsigned r = item % per_pass, w = r % FUSED_TILES;
-                s = r / FUSED_TILES;
-                tau = (w % 256u) * TILE_CLASSES + w / 256u;        // a pass emits its tile classes in turn
-                have_item = true;
-                spins = 0;
-                if (n < m.npasses) {
-                    TRACE(n, tau, 0);
-                    // the pass table does not depend on anything that is still running
-                    const uint4 *src = reinterpret_cast<const uint4 *>(m.ctx[s].passtab + (size_t)n * PASSTAB_WORDS);
-                    for (unsigned e = lane; e < PASSTAB_WORDS / 4; e += 32) reinterpret_cast<uint4 *>(sm.tab[b])[e] = __ldcg(src + e);
-                }
+        TRACE(TKEY(n, s), tau, 0);
+        const PersistArgs &a = m.ctx[s];
+        PersistCtl &pc = a.ctl->pc;
+        if (!BULK_LOAD) {
+            // the pass table does not depend on anything that is still running (bulk mode: it travels with the tile)
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.passtab + (size_t)n * PASSTAB_WORDS);
+            for (unsigned e = lane; e < PASSTAB_WORDS / 4; e += 32) reinterpret_cast<uint4 *>(sm.tab[b])[e] = __ldcg(src + e);
+        }
+        unsigned long long pw = 0;
+        bool stopped = false;
+        for (unsigned spins = 0;; spins++) {
+            // one round of parallel loads: pass parameters, stop mark, the previous pass's completion counters
+            unsigned long long v = 0;
+            if (lane == 0) v = ld_relaxed64(&pc.slot[n % PSLOTS].pass_word);
+            if (lane == 1) v = ld_relaxed(&pc.stop_pass);
+            if (lane == 2 && n > 0) v = ld_relaxed64(&pc.slot[(n - 1) % PSLOTS].done_word);
+            pw = __shfl_sync(0xffffffffu, v, 0);
+            const int stop = (int)(unsigned)__shfl_sync(0xffffffffu, v, 1);
+            const unsigned long long dwd = __shfl_sync(0xffffffffu, v, 2);
+            stopped = n >= stop;
+            // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
+            const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) && (n == 0 || done_class_count(dwd, tau >> 8) >= 256u);
+            if (stopped || ready) break;
+            if (spins > SPIN_LIMIT) {            // a wait that lasts seconds means a broken invariant: flag it, never hang the GPU
+                if (lane == 0) { atomicOr((unsigned *)&a.ctl->error, 16u); atomicMin(&pc.stop_pass, 0); }
+                stopped = true;
+                break;
             }
-            if (n >= m.npasses) {
-                // no more work: tell the compute warps (they leave without arriving on done[b], so this slot is not a tile)
-                if (lane == 0) sm.info[b].go = -1;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full[b]);
-                exiting = true;
-                progress = true;
+            __nanosleep(60);
+        }
+        fence_acq_rel();                           // acquire: the producers' metric stores, the pass parameters
+        if (BULK_LOAD) fence_proxy_async();        // ... which the bulk-copy engine (async proxy) is about to read
+        const int cur = (a.cur0 + n) % NBUF;       // buffers advance by one per resolved pass
+        if (lane == 0) {
+            TileInfo &ti = sm.info[b];
+            ti.oldm = a.metrics[cur];
+            ti.newm = a.metrics[(cur + 1) % NBUF];
+            ti.ring = a.ring;
+            ti.st = &pc.slot[n % PSLOTS].st;
+            ti.tau = tau;
+            ti.sub2 = (uint32_t)(pw & 0x7fffffffu) * 0x10001u;
+            ti.careful = (int)((pw >> 31) & 1u);
+            ti.go = stopped ? 0 : 1;
+            ti.n = n;
+            ti.s = (int)s;
+            TRACE(TKEY(n, s), tau, 1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (BULK_LOAD && !stopped) {
+                // pass table (1 KiB) and tile (256 rows x 128 bytes, rows 64 KiB apart, one tensor copy) -> shared memory;
+                // the hand-over completes when the bytes have landed
+                mbar_arrive_expect_tx(&sm.full[b], 256u * 128u + PASSTAB_WORDS * 4u);
+                bulk_g2s(sm.tab[b], a.passtab + (size_t)n * PASSTAB_WORDS, PASSTAB_WORDS * 4u, &sm.full[b]);
+                tma_load_tile(sm.tile[k & 1], reinterpret_cast<const uint8_t *>(a.tmaps) + (size_t)cur * TMAP_BYTES, (int)(tau * FUSED_TILE_COLS), &sm.full[b]);
             } else {
-                const PersistArgs &a = m.ctx[s];
-                PersistCtl &pc = a.ctl->pc;
-                // one round of parallel loads: pass parameters, stop mark, the previous pass's completion counters
-                unsigned long long v = 0;
-                if (lane == 0) v = ld_relaxed64(&pc.slot[n % PSLOTS].pass_word);
-                if (lane == 1) v = ld_relaxed(&pc.stop_pass);
-                if (lane == 2 && n > 0) v = ld_relaxed64(&pc.slot[(n - 1) % PSLOTS].done_word);
-                const unsigned long long pw = __shfl_sync(0xffffffffu, v, 0);
-                const int stop = (int)(unsigned)__shfl_sync(0xffffffffu, v, 1);
-                const unsigned long long dwd = __shfl_sync(0xffffffffu, v, 2);
-                bool stopped = n >= stop;
-                // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
-                const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) && (n == 0 || done_class_count(dwd, tau >> 8) >= 256u);
-                if (!stopped && !ready && ++spins > SPIN_LIMIT) {
-                    if (lane == 0) { atomicOr((unsigned *)&a.ctl->error, 16u); atomicMin(&pc.stop_pass, 0); }
-                    stopped = true;
-                }
-                if (stopped || ready) {
-                    fence_acq_rel();                           // acquire: the producers' metric stores, the pass parameters
-                    if (BULK_LOAD) fence_proxy_async();        // ... which the bulk-copy engine (async proxy) is about to read
-                    if (lane == 0) {
-                        TileInfo &ti = sm.info[b];
-                        const int cur = (a.cur0 + n) % NBUF;    // buffers advance by one per resolved pass
-                        ti.oldm = a.metrics[cur];
-                        ti.newm = a.metrics[(cur + 1) % NBUF];
-                        ti.ring = a.ring;
-                        ti.st = &pc.slot[n % PSLOTS].st;
-                        ti.tau = tau;
-                        ti.sub2 = (uint32_t)(pw & 0x7fffffffu) * 0x10001u;
-                        ti.careful = (int)((pw >> 31) & 1u);
-                        ti.go = stopped ? 0 : 1;
-                        ti.n = n;
-                        ti.s = (int)s;
-                        TRACE(n, tau, 1);
-                    }
-                    __syncwarp();
-                    if (BULK_LOAD && !stopped) {
-                        // the tile (256 rows x 128 bytes, rows 64 KiB apart) -> shared memory in one tensor copy; the hand-over
-                        // completes when the bytes have landed
-                        if (lane == 0) {
-                            mbar_arrive_expect_tx(&sm.full[b], 256u * 128u);
-                            const int cur = (a.cur0 + n) % NBUF;
-                            tma_load_tile(sm.tile[k_prep & 1], reinterpret_cast<const uint8_t *>(a.tmaps) + (size_t)cur * TMAP_BYTES, (int)(tau * FUSED_TILE_COLS), &sm.full[b]);
-                        }
-                    } else if (lane == 0) {
-                        mbar_arrive(&sm.full[b]);
-                    }
-                    k_prep++;
-                    have_item = false;
-                    progress = true;
-                }
+                mbar_arrive(&sm.full[b]);
             }
         }
-        // ---- C'. throughput mode: the finished tile is published after the hand-over attempt ----
-        if (pend) {
-            if (p_go > 0 && lane == 0) {
-                Ctl *c = m.ctx[p_s].ctl;
-                PassSlot &sl = c->pc.slot[p_n % PSLOTS];
-                const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(p_tau % TILE_CLASSES));
-                TRACE(p_n, p_tau, 6);
-                if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, p_n);
-                TRACE(p_n, p_tau, 7);
-            }
-            __syncwarp();
-            pend = false;
-            progress = true;
-        }
-        if (!progress) __nanosleep(k_done < k_prep ? 40 : 100);   // a running tile to watch for / only dependencies to wait for
+        __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_persist(MultiArgs m)
+__device__ void retirer_warp(FusedSmem &sm, const MultiArgs &m)
+{
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned k = 0;; k++) {
+        const unsigned b = k % NSLOT, par = (k / NSLOT) & 1;
+        mbar_wait(&sm.full[b], par);
+        const TileInfo &ti = sm.info[b];
+        const int go = ti.go, n = ti.n, s = ti.s;
+        const unsigned tau = ti.tau;
+        if (go < 0) return;
+        mbar_wait(&sm.done[b], par);               // every compute warp has issued the tile's stores and is done with the slot
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.slotfree[b]);
+        if (go > 0 && lane == 0) {
+            Ctl *c = m.ctx[s].ctl;
+            PassSlot &sl = c->pc.slot[n % PSLOTS];
+            // release: the compute warps' stores (ordered before this thread by the mbarrier) become visible GPU-wide
+            // before the tile counts as done
+            const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(tau % TILE_CLASSES));
+            TRACE(TKEY(n, s), tau, 6);
+            if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, n);
+            TRACE(TKEY(n, s), tau, 7);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, FUSED_CTAS_PER_SM) k_acs_persist(MultiArgs m)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.full[i], 1); mbar_init(&sm.done[i], FUSED_THREADS / 32); }
+        for (int i = 0; i < NSLOT; i++) mbar_init(&sm.slotfree[i], 1);
         mbar_init(&sm.freeb[0], FUSED_THREADS / 32); mbar_init(&sm.freeb[1], FUSED_THREADS / 32);
     }
     __syncthreads();
     if (tid >= FUSED_THREADS) {
-        protocol_warp(sm, m);
+        if (tid < FUSED_THREADS + 32) producer_warp(sm, m);
+        else retirer_warp(sm, m);
         return;
     }
     for (unsigned k = 0;; k++) {
@@ -623,8 +582,8 @@ __global__ void __launch_bounds__(FUSED_THREADS + 32, FUSED_CTAS_PER_SM) k_acs_p
         if (go < 0) break;
         if (go > 0) {
             uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? (k & 1) : 0];
-            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
-            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], ti.n);
+            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], TKEY(ti.n, ti.s));
+            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], TKEY(ti.n, ti.s));
         } else {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.freeb[k & 1]);     // a skipped tile still hands its buffer on
@@ -678,7 +637,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, FUSED_THREADS + 32, sizeof(FusedSmem));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, CTA_THREADS, sizeof(FusedSmem));
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -692,7 +651,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     }
     const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
     const int grid = (int)(items < slots[dev] ? items : slots[dev]);
-    k_acs_persist<<<grid, FUSED_THREADS + 32, sizeof(FusedSmem), st>>>(m);
+    k_acs_persist<<<grid, CTA_THREADS, sizeof(FusedSmem), st>>>(m);
     return cudaGetLastError();
 }
 

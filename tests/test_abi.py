@@ -91,3 +91,16 @@ def test_reference_callers_link_unchanged():
         assert "create_viterbi224" in out and "update_viterbi224_blk" in out
         dyn = subprocess.run(["readelf", "-d", os.path.join(ref, exe)], capture_output=True, text=True).stdout
         assert "libviterbi224_b200.so" in dyn
+
+
+def test_block_driver_is_built_and_fails_loudly_without_a_gpu(built):
+    """isee3-decoder_b200/bin/vdecode_block links against the in-tree library (relative rpath) and, on a box without a
+    CUDA device, refuses to run instead of falling back to anything: exit code 1 and the library's reason on stderr."""
+    exe = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    assert os.path.exists(exe)
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libviterbi224_b200.so" in ldd and "not found" not in ldd
+    if v224.device_count() == 0:
+        r = subprocess.run([exe, "-q"], input=b"\x80" * 64, capture_output=True, timeout=60)
+        assert r.returncode == 1 and r.stdout == b""
+        assert b"create_viterbi224 failed" in r.stderr and b"no CUDA device" in r.stderr
