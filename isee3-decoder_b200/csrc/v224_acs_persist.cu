@@ -147,8 +147,9 @@ struct TileInfo {
     uint32_t sub2;       // sub in both halves
     int go;              // 1 run the tile, 0 skip it (decoder stopped), -1 no more work
     int careful;
-    int n, s;            // pass and decoder (protocol warp's own bookkeeping)
-    int pad[2];
+    int n, s;            // pass and decoder (the protocol warps' own bookkeeping)
+    uint32_t lab;        // packed_tile_labels(tau): the tile's part of every stage's branch label
+    int pad;
 };
 // Tile k of a CTA uses bookkeeping slot k % NSLOT (info, pass table, full/done barriers) and data buffer k % XCHG_BUFS.
 // A data buffer is free again as soon as the tile's round-2 reads are over (`freeb`), long before its stores are out
@@ -194,11 +195,11 @@ __global__ void __launch_bounds__(PASSTAB_WORDS) k_build_passtab(uint32_t *tab, 
 // compute warps: one tile, eight stages
 // ------------------------------------------------------------------------------------------
 template <int T, bool CAREFUL>
-__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *tab, uint32_t *s0, uint32_t *ring_chunk,
+__device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *tab, uint32_t *s0, uint32_t *ring_chunk,
                                             PassStats *st)
 {
     uint32_t dw[NQ];
-    acs_stage<T>(A, pbase, tab, dw);
+    acs_stage<T>(A, labels, tab, dw);
     uint32_t *dst = ring_chunk + (size_t)tab[OPTAB_WORDS + T - 1] * ROWWORDS;
     if (NQ == 4) st_cs_v4(dst, make_uint4(dw[0], dw[1], dw[NQ - 2], dw[NQ - 1]));
     else         st_cs_v2(dst, dw[0], dw[1]);
@@ -219,9 +220,11 @@ __device__ __forceinline__ uint32_t xchg_index(uint32_t m, uint32_t g)
 // Tile `tau` = columns [64 tau, 64 tau + 64) of all 256 rows.  Metrics are read through L2 only (another SM wrote
 // them, possibly within this launch).  `xbuf` = this tile's exchange buffer.
 template <bool CAREFUL>
-__device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, uint64_t *freeb, int trace_n)
+__device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, uint64_t *freeb, uint32_t labthr,
+                                           int trace_n)
 {
     const uint32_t tid = threadIdx.x, tau = ti.tau, sub = ti.sub2;
+    const uint32_t labels = labthr ^ ti.lab;               // this thread's branch label of every stage, two bits each
     PassStats *st = ti.st;
     uint32_t *ring_chunk = ti.ring + (size_t)(tau * FUSED_THREADS + tid) * NQ;      // see fused_bit_address()
     uint32_t A[16][NQ];
@@ -257,11 +260,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             }
         }
         TRACE(trace_n, tau, 2);
-        const uint32_t pbase = (thr << 15) | (G << COLW_LOG2);
-        fused_stage<1, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<2, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<3, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<4, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<1, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<2, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<3, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<4, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
         // ---- exchange: rows m = mh*16 + ml ----
         // The exchange happens in place: a thread writes exactly the rows it read (the swizzle only moves elements
         // between lanes of its own warp).  With a single buffer the previous tile's round-2 reads must be over.
@@ -298,11 +300,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             if ((tid & 31) == 0) mbar_arrive(freeb);
         }
         TRACE(trace_n, tau, 3);
-        const uint32_t pbase = (thr << 19) | (G << COLW_LOG2);
-        fused_stage<5, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<6, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<7, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
-        fused_stage<8, CAREFUL>(A, pbase, tab, s0, ring_chunk, st);
+        fused_stage<5, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<6, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<7, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<8, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
         TRACE(trace_n, tau, 4);
         // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B, four lanes = one line ----
         {
@@ -513,6 +514,7 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
             ti.go = stopped ? 0 : 1;
             ti.n = n;
             ti.s = (int)s;
+            ti.lab = packed_tile_labels(tau << FUSED_COLS_LOG2);
             TRACE(TKEY(n, s), tau, 1);
         }
         __syncwarp();
@@ -574,6 +576,14 @@ __global__ void __launch_bounds__(CTA_THREADS, FUSED_CTAS_PER_SM) k_acs_persist(
         else retirer_warp(sm, m);
         return;
     }
+    // the thread's own part of the branch labels (its row / column group in round 1 and in round 2), fixed for the kernel
+    uint32_t labthr;
+    {
+        uint32_t t1, g1, t2, g2;
+        round1_map(tid, t1, g1);
+        round2_map(tid, t2, g2);
+        labthr = packed_thread_labels((t1 << 15) | (g1 << COLW_LOG2), (t2 << 19) | (g2 << COLW_LOG2));
+    }
     for (unsigned k = 0;; k++) {
         const unsigned b = k % NSLOT;
         mbar_wait(&sm.full[b], (k / NSLOT) & 1);
@@ -582,8 +592,8 @@ __global__ void __launch_bounds__(CTA_THREADS, FUSED_CTAS_PER_SM) k_acs_persist(
         if (go < 0) break;
         if (go > 0) {
             uint32_t *xbuf = sm.tile[XCHG_BUFS == 2 ? (k & 1) : 0];
-            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], TKEY(ti.n, ti.s));
-            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], TKEY(ti.n, ti.s));
+            if (ti.careful) fused_tile<true>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], labthr, TKEY(ti.n, ti.s));
+            else            fused_tile<false>(xbuf, sm.tab[b], sm.s0, ti, &sm.freeb[k & 1], labthr, TKEY(ti.n, ti.s));
         } else {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.freeb[k & 1]);     // a skipped tile still hands its buffer on

@@ -184,7 +184,10 @@ __host__ __device__ inline uint32_t round2_tid(uint32_t thr, uint32_t g)
     return (w << 5) | lane;
 }
 
-// Decision-row formats: 0 = canonical; t (1..8) = written by stage t of a fused pass.
+// Decision-row formats: 0 = canonical; t (1..8) = written by stage t of a fused pass.  Fused rows hold the COMPLEMENT of
+// the decision bit (the sign bit the butterfly produces is the inverted decision; flipping it once per traceback read
+// is cheaper than once per state update).
+constexpr uint32_t FUSED_ROWS_COMPLEMENTED = 1u;
 // Where a fused-format decision bit lives: state s after stage t -> bit index inside the 2^23-bit row.
 // Slot fields (23 bits): mh[4] | ml[4] | j[15], j = tile[9] | g | q | h.  The thread (tile, tid) owns the NQ
 // consecutive words starting at word (tile * FUSED_THREADS + tid) * NQ; inside them

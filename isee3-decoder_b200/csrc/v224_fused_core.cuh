@@ -104,6 +104,27 @@ template <int T> V224_HD uint32_t slot_label(uint32_t p)
 }
 constexpr uint32_t FLIP_LABEL = (uint32_t)G1FLIP | ((uint32_t)G2FLIP << 1);
 
+// The label is linear in the slot bits, so a thread's label at stage t is
+//   label_t(thread bits) ^ label_t(tile bits) ^ FLIP_LABEL
+// with disjoint thread / tile bit fields.  Both parts are packed two bits per stage (stage t at bits 2t-2, 2t-1):
+// the thread part once per kernel, the tile part (with the flip folded in) once per tile -- a stage then needs one
+// shift and one mask instead of the parities.
+template <int T> V224_HD uint32_t packed_label_stage(uint32_t p) { return slot_label<T>(p) << (2 * (T - 1)); }
+// stages 1..FR see round-1 thread bits p1, stages FR+1..FK round-2 thread bits p2
+V224_HD uint32_t packed_thread_labels(uint32_t p1, uint32_t p2)
+{
+    return packed_label_stage<1>(p1) | packed_label_stage<2>(p1) | packed_label_stage<3>(p1) | packed_label_stage<4>(p1) |
+           packed_label_stage<5>(p2) | packed_label_stage<6>(p2) | packed_label_stage<7>(p2) | packed_label_stage<8>(p2);
+}
+V224_HD uint32_t packed_tile_labels(uint32_t ptile)
+{
+    uint32_t flip = 0;
+    for (int t = 0; t < FK; t++) flip |= FLIP_LABEL << (2 * t);
+    return (packed_label_stage<1>(ptile) | packed_label_stage<2>(ptile) | packed_label_stage<3>(ptile) | packed_label_stage<4>(ptile) |
+            packed_label_stage<5>(ptile) | packed_label_stage<6>(ptile) | packed_label_stage<7>(ptile) | packed_label_stage<8>(ptile)) ^ flip;
+}
+static_assert(FK == 8 && FR == 4, "packed labels are written out for 8 stages in two rounds");
+
 // Operand table in shared memory: optab[(t-1)*32 + beta*8 + {0..3: X[beta^i], 4..7: K[beta^i]}].
 // The per-pass table in global memory (PassTab) carries it plus the ring rows of the pass's eight stages.
 constexpr int OPTAB_WORDS = FK * 32;
@@ -129,16 +150,17 @@ V224_HD uint32_t optab_entry(int e, SymPtr sym)
 
 // One trellis stage over a thread's 16 rows x NQ packed registers.
 //   A[inner][q]  : packed P metrics, halves = columns 2q, 2q+1 of the thread's 2*NQ columns
-//   pbase        : the thread's slot bits outside (inner, q, h)
+//   labels       : packed_thread_labels(..) ^ packed_tile_labels(..): the thread's label (flip included) of stage t at bits 2t-2, 2t-1
 //   optab        : shared operand table
 //   dw[NQ]       : returns the 32*NQ decision bits of this thread/stage in fused layout (fused_bit_address())
 template <int T>
-V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *optab, uint32_t (&dw)[NQ])
+V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *optab, uint32_t (&dw)[NQ])
 {
     constexpr int sb = FR - 1 - ((T - 1) % FR);          // stage bit inside `inner`
     constexpr int ishift = (T <= FR) ? 19 : 15;           // slot position of `inner`
-    const uint32_t beta = slot_label<T>(pbase) ^ FLIP_LABEL;
-    const uint32_t *tab = optab + (T - 1) * 32 + beta * 8;
+    // operand row of this thread's label: (T-1)*32 + beta*8 words
+    const uint32_t boff = (T == 1 ? (labels << 3) : T <= 2 ? (labels << 1) : (labels >> (2 * (T - 1) - 3))) & 24u;
+    const uint32_t *tab = optab + (T - 1) * 32 + boff;
     uint32_t Xv[4], Kv[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { Xv[i] = tab[i]; Kv[i] = tab[4 + i]; }
@@ -165,13 +187,15 @@ V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *op
             A[ia][q] = f_addmin_u16x2(a, X, t0);          // min(m0, m1) -> state 2b    (:319)
             A[ic][q] = f_addmin_u16x2(a, Y, t1);          // min(m2, m3) -> state 2b+1  (:320)
         }
-        // gather the (inverted) sign bits: word = side * NQ/2 + q/2, byte = (q&1)*2 + half, bit = pair index
+        // gather the sign bits: word = side * NQ/2 + q/2, byte = (q&1)*2 + half, bit = pair index
 #pragma unroll
         for (int qq = 0; qq < NQ / 2; qq++) {
             const uint32_t s0 = f_prmt(D0[2 * qq], D0[2 * qq + 1], 0xfdb9);
             const uint32_t s1 = f_prmt(D1[2 * qq], D1[2 * qq + 1], 0xfdb9);
-            dw[qq] = (~s0 & (0x01010101u << pidx)) | dw[qq];
-            dw[NQ / 2 + qq] = (~s1 & (0x01010101u << pidx)) | dw[NQ / 2 + qq];
+            // bit 15 of D is the INVERTED decision; it is stored as it is (fused rows hold complemented bits, the
+            // traceback kernels flip them back: FUSED_ROWS_COMPLEMENTED) -- one LOP3 per 4 decisions, no final XOR
+            dw[qq] = (s0 & (0x01010101u << pidx)) | dw[qq];
+            dw[NQ / 2 + qq] = (s1 & (0x01010101u << pidx)) | dw[NQ / 2 + qq];
         }
     }
 }

@@ -181,7 +181,8 @@ __device__ __forceinline__ uint32_t read_decision(const uint32_t *ring, const ui
 {
     const uint8_t f = row_fmt[row];
     const uint32_t bit = f == ROWFMT_CANON ? state : fused_bit_address(f, state);
-    return (ring[(size_t)row * ROWWORDS + (bit >> 5)] >> (bit & 31)) & 1u;     // viterbi224_sse2.c:141
+    const uint32_t flip = f == ROWFMT_CANON ? 0u : FUSED_ROWS_COMPLEMENTED;
+    return ((ring[(size_t)row * ROWWORDS + (bit >> 5)] >> (bit & 31)) & 1u) ^ flip;     // viterbi224_sse2.c:141
 }
 
 // Speculative segment walk.  Segment i covers bits [i*L, min((i+1)*L, nbits)).  Its end state is
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) k_export_row(TraceArgs a, long long row, 
     uint32_t v = 0;
     for (int b = 0; b < 32; b++) {
         const uint32_t addr = fused_bit_address(f, w * 32 + b);
-        v |= ((r[addr >> 5] >> (addr & 31)) & 1u) << b;
+        v |= (((r[addr >> 5] >> (addr & 31)) & 1u) ^ FUSED_ROWS_COMPLEMENTED) << b;
     }
     out[w] = v;
 }

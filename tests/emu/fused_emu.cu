@@ -12,11 +12,11 @@
 using namespace v224;
 
 template <int T>
-static void emu_stage(uint32_t (&A)[16][NQ], uint32_t pbase, const uint32_t *optab, uint32_t *rows, uint32_t chunk,
+static void emu_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *optab, uint32_t *rows, uint32_t chunk,
                       uint32_t *s0, uint32_t *minP, bool first)
 {
     uint32_t dw[NQ];
-    acs_stage<T>(A, pbase, optab, dw);
+    acs_stage<T>(A, labels, optab, dw);
     uint32_t *row = rows + (size_t)(T - 1) * ROWWORDS;
     for (int w = 0; w < NQ; w++) row[chunk * NQ + w] = dw[w];
     if (first) s0[T] = A[0][0] & 0xffffu;
@@ -56,12 +56,16 @@ void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const 
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(oldP + ((size_t)(mh * 16 + thr) * 32768 + G * COLW));
                 for (int q = 0; q < NQ; q++) A[mh][q] = src[q] - sub2;
             }
-            const uint32_t pbase = (thr << 15) | (G << COLW_LOG2);
+            // the kernel's split of the branch labels: thread part (fixed per thread) ^ tile part (per tile, from the producer warp)
+            uint32_t t2, g2;
+            round2_map(tid, t2, g2);
+            const uint32_t labels = packed_thread_labels((thr << 15) | (g << COLW_LOG2), (t2 << 19) | (g2 << COLW_LOG2)) ^
+                                    packed_tile_labels(tau << FUSED_COLS_LOG2);
             const bool first = tau == 0 && tid == 0;
-            emu_stage<1>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<2>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<3>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<4>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<1>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<2>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<3>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<4>(A, labels, optab, rows, chunk, s0, minP, first);
             for (int mh = 0; mh < 16; mh++)
                 for (int q = 0; q < NQ; q++) tile[xchg_index(mh * 16 + thr, g) * NQ + q] = A[mh][q];
         }
@@ -73,12 +77,15 @@ void emu_fused_pass(const uint16_t *oldP, uint16_t *newP, uint32_t *rows, const 
             uint32_t A[16][NQ];
             for (int ml = 0; ml < 16; ml++)
                 for (int q = 0; q < NQ; q++) A[ml][q] = tile[xchg_index(thr * 16 + ml, g) * NQ + q];
-            const uint32_t pbase = (thr << 19) | (G << COLW_LOG2);
+            uint32_t t1, g1;
+            round1_map(tid, t1, g1);
+            const uint32_t labels = packed_thread_labels((t1 << 15) | (g1 << COLW_LOG2), (thr << 19) | (g << COLW_LOG2)) ^
+                                    packed_tile_labels(tau << FUSED_COLS_LOG2);
             const bool first = tau == 0 && tid == 0;
-            emu_stage<5>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<6>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<7>(A, pbase, optab, rows, chunk, s0, minP, first);
-            emu_stage<8>(A, pbase, optab, rows, chunk, s0, minP, first);
+            emu_stage<5>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<6>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<7>(A, labels, optab, rows, chunk, s0, minP, first);
+            emu_stage<8>(A, labels, optab, rows, chunk, s0, minP, first);
             uint32_t mx = tile_max(A);
             if (mx > maxP) maxP = mx;
             for (int q = 0; q < NQ; q++)
@@ -97,7 +104,7 @@ void emu_canon_row(int fmt, const uint32_t *fused_row, uint32_t *canon_row)
     memset(canon_row, 0, ROWBYTES);
     for (uint32_t s = 0; s < NSTATES; s++) {
         const uint32_t a = fused_bit_address(fmt, s);
-        canon_row[s >> 5] |= ((fused_row[a >> 5] >> (a & 31)) & 1u) << (s & 31);
+        canon_row[s >> 5] |= (((fused_row[a >> 5] >> (a & 31)) & 1u) ^ FUSED_ROWS_COMPLEMENTED) << (s & 31);
     }
 }
 }
