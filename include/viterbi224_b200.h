@@ -68,6 +68,16 @@ int v224x_stream_decode_seg(void *p, const unsigned char *syms, int nbits, int d
 int v224x_stream_decode_seg_dev(void *p, const unsigned char *dev_syms, int nbits, int delay, unsigned char *dev_bits_out, int nseg,
                                 int conv, v224x_seg_report *report);
 
+/* A batch of independent frames, each decoded exactly as the reference's three-call sequence would decode it
+ *     init_viterbi224(p, start_states[f]); update_viterbi224_blk(p, syms + 2*framebits*f, framebits);
+ *     chainback_viterbi224(p, data_out + ceil(framebits/8)*f, framebits, end_states[f]);
+ * (vtest224.c:116-118, hybridtest.c:186-193, decode.c:220-222), with up to nlock (1..4, <= 0: 3) frames side by side in
+ * one persistent launch.  start_states / end_states may be NULL (all 0).  Needs framebits <= the handle's len.
+ * Afterwards the handle holds the state of the last frame of its lane (as after that frame's chainback).
+ * Returns 0, -1 on error. */
+int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int framebits, const unsigned int *start_states,
+                        const unsigned int *end_states, unsigned char *data_out, int nlock);
+
 /* init variant for time-segmented decoding: every metric = SHRT_MIN + bias and no state is
  * favoured (start_state < 0), or init_viterbi224 semantics (start_state >= 0). */
 int v224x_init_uniform(void *p, int bias, int start_state);

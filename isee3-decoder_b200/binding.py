@@ -14,7 +14,7 @@ ABI_SYMBOLS = ["create_viterbi224", "init_viterbi224", "update_viterbi224_blk", 
                "decodebit_viterbi224", "decodeword_viterbi224", "max_metric_viterbi224", "min_metric_viterbi224",
                "delete_viterbi224"]
 EXT_SYMBOLS = ["v224x_device_count", "v224x_set_device", "v224x_last_error", "v224x_version", "v224x_stream_decode",
-               "v224x_stream_decode_dev", "v224x_stream_decode_seg", "v224x_stream_decode_seg_dev", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
+               "v224x_stream_decode_dev", "v224x_stream_decode_seg", "v224x_stream_decode_seg_dev", "v224x_decode_frames", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
                "v224x_h2d", "v224x_d2h", "v224x_host_alloc_pinned", "v224x_host_free_pinned", "v224x_timer_start",
                "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms", "v224x_kernel_time_passes",
                "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option"]
@@ -71,6 +71,7 @@ def load_library():
         "v224x_stream_decode_dev": (ci, [vp, vp, ci, ci, vp]),
         "v224x_stream_decode_seg": (ci, [vp, vp, ci, ci, vp, ci, ci, vp]),
         "v224x_stream_decode_seg_dev": (ci, [vp, vp, ci, ci, vp, ci, ci, vp]),
+        "v224x_decode_frames": (ci, [vp, vp, ci, ci, vp, vp, vp, ci]),
         "v224x_update_dev": (ci, [vp, vp, ci]),
         "v224x_update_multi_dev": (ci, [vp, vp, ci, ci, vp]),
         "v224x_init_uniform": (ci, [vp, ci, ci]),
@@ -204,6 +205,20 @@ class Viterbi224:
         self._check(self.lib.v224x_stream_decode_seg_dev(self.h, dev_syms, int(nbits), int(delay), dev_bits, int(nseg), int(conv),
                                                          ctypes.byref(rep)), "v224x_stream_decode_seg_dev")
         return {k: getattr(rep, k) for k, _ in SegReport._fields_}
+
+    def decode_frames(self, syms, nframes, framebits, start_states=None, end_states=None, nlock=3):
+        """v224x_decode_frames: nframes independent frames (init / update / chainback each), nlock side by side.
+        Returns uint8[nframes, ceil(framebits/8)]."""
+        a, p = _u8(syms)
+        assert a.size >= 2 * nframes * framebits
+        out = np.empty((nframes, (framebits + 7) // 8), dtype=np.uint8)
+        ss = None if start_states is None else np.ascontiguousarray(start_states, dtype=np.uint32)
+        es = None if end_states is None else np.ascontiguousarray(end_states, dtype=np.uint32)
+        self._check(self.lib.v224x_decode_frames(self.h, p, int(nframes), int(framebits),
+                                                 None if ss is None else ss.ctypes.data_as(ctypes.c_void_p),
+                                                 None if es is None else es.ctypes.data_as(ctypes.c_void_p),
+                                                 out.ctypes.data_as(ctypes.c_void_p), int(nlock)), "v224x_decode_frames")
+        return out
 
     def dev_alloc(self, nbytes):
         p = self.lib.v224x_dev_alloc(self.h, int(nbytes))

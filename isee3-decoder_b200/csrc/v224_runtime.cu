@@ -473,6 +473,59 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
     return 0;
 }
 
+// ---- batched frame decode -------------------------------------------------------------------
+// The reference's frame callers (vtest224.c:116-118, hybridtest.c:186-193, decode.c:220-222) decode one frame at a
+// time: init(start) / update(framebits) / chainback(framebits, end).  Frames are independent, so a batch of them is
+// another natural axis for the lockstep launch: up to MAX_CTX decoders run one frame each side by side (the CTAs that
+// would wait at one frame's pass boundary work on another frame's tiles).  Every frame is decoded exactly as the
+// three-call sequence would decode it.
+int frames_core(Decoder *d, const uint8_t *host_syms, int nframes, int framebits, const unsigned *start_states, const unsigned *end_states,
+                uint8_t *host_data, int nlock)
+{
+    if (framebits <= 0 || framebits > d->len) { set_err("frame decode needs 0 < framebits <= len (framebits %d, len %d)", framebits, d->len); return -1; }
+    const int S = std::max(1, std::min(std::min(nlock, MAX_CTX), nframes));
+    const size_t fsyms = 2 * (size_t)framebits, fbytes = ((size_t)framebits + 7) / 8;
+    Decoder *D[MAX_CTX] = {d};
+    for (int i = 1; i < S; i++) {
+        if (!d->aux[i - 1]) d->aux[i - 1] = make_aux(d);
+        D[i] = d->aux[i - 1];
+        if (!D[i]) { set_err("frame decode: cannot create decoder %d of %d: %s", i, S, g_err); return -1; }
+    }
+    if (grow((void **)&d->dsyms, &d->dsyms_cap, fsyms * (size_t)nframes)) return -1;
+    if (grow((void **)&d->dout, &d->dout_cap, fbytes * (size_t)nframes)) return -1;
+    cudaStream_t st = d->stream;
+    CU(cudaMemcpyAsync(d->dsyms, host_syms, fsyms * (size_t)nframes, cudaMemcpyHostToDevice, st));
+    const int L = std::max(8, d->chain_seg & ~7);
+    const uint32_t nseg = ((uint32_t)framebits + L - 1) / L;
+    for (int i = 0; i < S; i++) {
+        if (grow((void **)&D[i]->seg, &D[i]->seg_cap, 2 * (size_t)nseg * sizeof(uint32_t))) return -1;
+        CU(cudaStreamSynchronize(D[i]->stream));
+    }
+    for (int f0 = 0; f0 < nframes; f0 += S) {
+        const int nb = std::min(S, nframes - f0);
+        const uint8_t *sp[MAX_CTX];
+        for (int i = 0; i < nb; i++) {
+            D[i]->cache_valid = 0;
+            const uint32_t ss = (start_states ? start_states[f0 + i] : 0u) & STATEMASK;
+            CU(launch_init(D[i]->metrics[0], D[i]->ctl, ss, INIT_BIAS, 0, st));                 // init_viterbi224(start), viterbi224_sse2.c:37-53
+            CU(cudaMemcpyAsync(D[i]->h_ctl, D[i]->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, st));
+            sp[i] = d->dsyms + fsyms * (size_t)(f0 + i);
+        }
+        CU(cudaStreamSynchronize(st));
+        d->launches += nb;
+        if (multi_update_core(D, sp, nb, framebits, nullptr)) return -1;
+        for (int i = 0; i < nb; i++) {
+            const uint32_t es = end_states ? end_states[f0 + i] : 0u;
+            CU(launch_chainback(trace_args(D[i]), (uint32_t)framebits, es, L, d->chain_warm, d->dout + fbytes * (size_t)(f0 + i), D[i]->seg, D[i]->seg + nseg,
+                                D[i]->d_redo, st));
+            d->launches += 2;
+        }
+    }
+    CU(cudaMemcpyAsync(host_data, d->dout, fbytes * (size_t)nframes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 } // namespace
 
 // ==========================================================================================
@@ -762,6 +815,16 @@ int v224x_stream_decode_seg(void *p, const unsigned char *syms, int nbits, int d
     CU(cudaMemcpyAsync(bits_out, dout, (size_t)nbits, cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
     return 0;
+}
+
+int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int framebits, const unsigned int *start_states,
+                        const unsigned int *end_states, unsigned char *data_out, int nlock)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (nframes <= 0) return 0;
+    if (bind(d)) return -1;
+    return frames_core(d, syms, nframes, framebits, start_states, end_states, data_out, nlock <= 0 ? 3 : nlock);
 }
 
 void *v224x_dev_alloc(void *p, size_t bytes)

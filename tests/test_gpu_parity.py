@@ -393,6 +393,40 @@ def test_segmented_stream_failed_handover_is_redone_exactly():
     assert np.array_equal(short, want2)
 
 
+def test_batched_frames_equal_the_three_call_sequence():
+    """v224x_decode_frames: 7 independent 1024-bit frames (decode.c:220-222 pattern: known start and end state = the
+    sync word's low 24 bits; two frames at 1 dB, one with a wrong end state) decoded 3 side by side == each frame through
+    init / update / chainback on one decoder == the transmitted data where the channel allows."""
+    nframes, fb = 7, 1024
+    sync = v224.streams.SYNCWORD & 0xFFFFFF
+    rng = np.random.default_rng(606)
+    frames = v224.streams.telemetry_bits(nframes, rng).reshape(nframes, fb)
+    syms, starts, ends = [], [], []
+    state = sync                                         # the previous frame ended with the sync word
+    for f in range(nframes):
+        sym01, state_out = S.encode_bits(frames[f], state)
+        ebn0 = 1.0 if f in (2, 5) else 3.0
+        syms.append(S.awgn_symdemod(sym01, ebn0, rng))
+        starts.append(state & 0x7FFFFF)
+        ends.append(sync if f != 4 else 12345)
+        state = state_out
+    syms = np.concatenate(syms)
+    want = []
+    with v224.Viterbi224(fb) as d:
+        for f in range(nframes):
+            d.init(starts[f])
+            d.update_blk(syms[2 * fb * f:], fb)
+            want.append(d.chainback(fb, ends[f]))
+    with v224.Viterbi224(fb) as d:
+        got = d.decode_frames(syms, nframes, fb, starts, ends, nlock=3)
+        got1 = d.decode_frames(syms, nframes, fb, starts, ends, nlock=1)
+    for f in range(nframes):
+        assert np.array_equal(got[f], want[f]), f
+        assert np.array_equal(got1[f], want[f]), f
+        if f not in (2, 4, 5):
+            assert np.array_equal(got[f], np.packbits(frames[f])), f
+
+
 def _window_check(d, syms_tail, nstages, ring_rows, label):
     """SURVEY 8c checkpoint window: dump the GPU state, continue `nstages` on the CPU checker and on the GPU,
     compare renormalisation counts, every metric and every decision row."""
