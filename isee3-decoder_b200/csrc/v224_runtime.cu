@@ -46,6 +46,7 @@ struct PoolEntry { int dev; size_t bytes; void *ptr; };
 std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
 constexpr size_t POOL_MAX_ENTRIES = 4;
+constexpr size_t POOL_MAX_BYTES = (size_t)24 << 30;      // cached rings never hold more than this (oldest are released first)
 
 void *pool_get(int dev, size_t bytes)
 {
@@ -74,13 +75,19 @@ void *pool_get(int dev, size_t bytes)
 }
 void pool_put(int dev, size_t bytes, void *ptr)
 {
-    void *evict = nullptr;
+    std::vector<void *> evict;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         g_pool.push_back({dev, bytes, ptr});
-        if (g_pool.size() > POOL_MAX_ENTRIES) { evict = g_pool.front().ptr; g_pool.erase(g_pool.begin()); }
+        size_t total = 0;
+        for (auto &e : g_pool) total += e.bytes;
+        while (!g_pool.empty() && (g_pool.size() > POOL_MAX_ENTRIES || total > POOL_MAX_BYTES)) {
+            total -= g_pool.front().bytes;
+            evict.push_back(g_pool.front().ptr);
+            g_pool.erase(g_pool.begin());
+        }
     }
-    if (evict) cudaFree(evict);
+    for (void *q : evict) cudaFree(q);
 }
 
 struct Decoder {
