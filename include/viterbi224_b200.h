@@ -71,7 +71,7 @@ int v224x_stream_decode_seg_dev(void *p, const unsigned char *dev_syms, int nbit
 /* A batch of independent frames, each decoded exactly as the reference's three-call sequence would decode it
  *     init_viterbi224(p, start_states[f]); update_viterbi224_blk(p, syms + 2*framebits*f, framebits);
  *     chainback_viterbi224(p, data_out + ceil(framebits/8)*f, framebits, end_states[f]);
- * (vtest224.c:116-118, hybridtest.c:186-193, decode.c:220-222), with up to nlock (1..4, <= 0: 3) frames side by side in
+ * (vtest224.c:116-118, hybridtest.c:186-193, decode.c:220-222), with up to nlock (1..4, <= 0: 4) frames side by side in
  * one persistent launch.  start_states / end_states may be NULL (all 0).  Needs framebits <= the handle's len.
  * Afterwards the handle holds the state of the last frame of its lane (as after that frame's chainback).
  * Returns 0, -1 on error. */

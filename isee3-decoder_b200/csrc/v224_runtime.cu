@@ -831,7 +831,7 @@ int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int fra
     if (!d) return -1;
     if (nframes <= 0) return 0;
     if (bind(d)) return -1;
-    return frames_core(d, syms, nframes, framebits, start_states, end_states, data_out, nlock <= 0 ? 3 : nlock);
+    return frames_core(d, syms, nframes, framebits, start_states, end_states, data_out, nlock <= 0 ? 4 : nlock);
 }
 
 void *v224x_dev_alloc(void *p, size_t bytes)

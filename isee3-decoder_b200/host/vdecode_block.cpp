@@ -12,7 +12,7 @@
 // what the per-bit loop returns).  Everything vdecode derives from decoder output (start-up suppression, the
 // re-encode symbol-error tally, the status lines) is replayed per pair afterwards from values recorded on the way in.
 //
-// Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 3).
+// Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 4).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,7 +57,7 @@ struct PairRec {
 
 int main(int argc, char *argv[])
 {
-    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 3;
+    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4;
     long block = 262144;
     const char *lang = getenv("LANG");
     setlocale(LC_ALL, lang ? lang : "en_US.utf8");                       // vdecode.c:59-62 (thousands separators in the status line)
