@@ -12,7 +12,9 @@
 // what the per-bit loop returns).  Everything vdecode derives from decoder output (start-up suppression, the
 // re-encode symbol-error tally, the status lines) is replayed per pair afterwards from values recorded on the way in.
 //
-// Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 4).
+// Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 4),
+// -P  pairs only: write the symbol pairs that would go to the decoder (2 bytes each) to stdout and exit -- no GPU needed;
+// the CPU test tier checks the pairing / phase-flip logic through it.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,12 +59,12 @@ struct PairRec {
 
 int main(int argc, char *argv[])
 {
-    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4;
+    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4, pairs_only = 0;
     long block = 262144;
     const char *lang = getenv("LANG");
     setlocale(LC_ALL, lang ? lang : "en_US.utf8");                       // vdecode.c:59-62 (thousands separators in the status line)
     int opt;
-    while ((opt = getopt(argc, argv, "d:pi:qFB:S:")) != -1) {
+    while ((opt = getopt(argc, argv, "d:pi:qFB:S:P")) != -1) {
         switch (opt) {
         case 'F': dontflip = 1; break;
         case 'q': quiet = 1; break;
@@ -71,6 +73,7 @@ int main(int argc, char *argv[])
         case 'd': delay = atoi(optarg); break;
         case 'B': block = atol(optarg); break;
         case 'S': nseg = atoi(optarg); break;
+        case 'P': pairs_only = 1; break;
         default: break;
         }
     }
@@ -82,9 +85,12 @@ int main(int argc, char *argv[])
     }
     if (block < 1024) block = 1024;
     const int ring_rows = delay + 8192;                                   // the library works through a block in chunks of (rows - delay)
-    void *vd = create_viterbi224(ring_rows);
-    if (!vd) { fprintf(stderr, "%s: create_viterbi224 failed: %s\n", argv[0], v224x_last_error()); return 1; }
-    init_viterbi224(vd, 0);                                               // vdecode.c:96
+    void *vd = nullptr;
+    if (!pairs_only) {
+        vd = create_viterbi224(ring_rows);
+        if (!vd) { fprintf(stderr, "%s: create_viterbi224 failed: %s\n", argv[0], v224x_last_error()); return 1; }
+        init_viterbi224(vd, 0);                                           // vdecode.c:96
+    }
 
     int taps[NTAPS];
     sync_taps(taps);
@@ -115,6 +121,13 @@ int main(int argc, char *argv[])
         }
         syms.resize(2 * (size_t)n);
         for (int i = 0; i < n; i++) { syms[2 * i] = pairs[i].s0; syms[2 * i + 1] = pairs[i].s1; }
+        if (pairs_only) {
+            fwrite(syms.data(), 1, syms.size(), stdout);
+            for (size_t f = 0; f < flip_at.size(); f++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
+            pairs.clear();
+            flip_at.clear();
+            return 0;
+        }
         bits.resize(n);
         if (v224x_stream_decode_seg(vd, syms.data(), n, delay, bits.data(), nseg, -1, nullptr) < 0) {
             fprintf(stderr, "%s: decode failed: %s\n", argv[0], v224x_last_error());
@@ -189,6 +202,7 @@ int main(int argc, char *argv[])
         }
     }
     if (flush_block()) return 1;
+    fflush(stdout);
     delete_viterbi224(vd);
     return 0;
 }

@@ -112,3 +112,24 @@ def test_two_rank_segmented_decode_gloo(built):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "RESULT diff=0 data_ok=True n=144" in outs[0], outs[0]
+
+
+def test_block_driver_pairing_equals_the_python_mirror(built):
+    """vdecode_block -P (pairs only, no GPU): the C++ host program's symbol pairing and phase-flip logic (its own
+    implementation of vdecode.c:101-140,186) against the Python mirror, which the GPU tier pins to the unmodified
+    reference's output: junk prefix (flip), a dropped symbol mid-stream (flip), -p start phase, -F no flipping."""
+    import subprocess
+    exe = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    bits, soft = v224.streams.telemetry_stream(14 * 1024, 3.0, seed=21, junk_symbols=77)
+    soft = np.delete(soft, 15_001)
+    for args, kw in ((["-q"], {}), (["-q", "-p"], {"start_phase": 1}), (["-q", "-F"], {"dontflip": True}), (["-q", "-B", "2000"], {})):
+        r = subprocess.run([exe, "-P"] + args, input=soft.tobytes(), capture_output=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        got = np.frombuffer(r.stdout, dtype=np.uint8).reshape(-1, 2)
+        want, flips = v224.vdecode.pair_symbols(soft, return_flips=True, **kw)
+        if kw.get("start_phase"):
+            want = want.copy(); got = got.copy()
+            want[0, 0] = got[0, 0] = 0          # -p: the first pair's even symbol is uninitialised in the reference
+        assert got.shape == want.shape and np.array_equal(got, want), args
+    r = subprocess.run([exe, "-P"], input=soft.tobytes(), capture_output=True, timeout=120)
+    assert r.stderr.count(b"flipping phase") == len(v224.vdecode.pair_symbols(soft, return_flips=True)[1]) >= 2
