@@ -126,6 +126,7 @@ struct Decoder {
     int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
+    long long stages_total;                // trellis stages ever run on this ring (how many rows a recycled decoder has to clear)
     double acs_ms;
     int time_kernels;
 };
@@ -164,6 +165,13 @@ int sync_ctl(Decoder *d)
     return 0;
 }
 
+// ---- recycled decoders: decode.c:216-229 creates and deletes a 1024-row decoder PER FRAME.  A create / delete pair
+// costs ~6 ms of allocations (pinned host memory, streams, events, tensor maps); a recycled decoder only clears the ring
+// rows it ever wrote and re-runs init.  At most DEC_POOL_MAX decoders wait here, none with auxiliary decoders attached. ----
+std::mutex g_dec_mu;
+std::vector<Decoder *> g_dec_pool;
+constexpr size_t DEC_POOL_MAX = 2;
+
 void destroy(Decoder *d)
 {
     if (!d) return;
@@ -201,6 +209,30 @@ int do_init(Decoder *d, int bias, int start_state)
 
 TraceArgs trace_args(Decoder *d) { return TraceArgs{d->ring, d->row_fmt, d->len}; }
 
+// A decoder from the recycle pool becomes indistinguishable from a freshly created one: default options, zero counters,
+// the ring rows it ever wrote read as zero again, init(0).
+int recycle(Decoder *d)
+{
+    if (bind(d)) return -1;
+    d->magic = MAGIC;
+    d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = 0;
+    d->chain_seg = 128;
+    d->chain_warm = 256;
+    d->launches = d->acs_launches_timed = d->acs_passes_timed = d->chainback_redo = 0;
+    d->acs_ms = 0;
+    d->time_kernels = 0;
+    const size_t rows = (size_t)std::min<long long>(d->len, std::max<long long>(0, d->stages_total));
+    if (rows) {
+        CU(cudaMemsetAsync(d->ring, 0, rows * ROWBYTES, d->stream));
+        CU(cudaMemsetAsync(d->row_fmt, 0, rows, d->stream));
+    }
+    CU(cudaMemsetAsync(d->ctl, 0, sizeof(Ctl), d->stream));
+    CU(cudaMemsetAsync(d->d_redo, 0, sizeof(unsigned), d->stream));
+    if (d->d_walk_steps) CU(cudaMemsetAsync(d->d_walk_steps, 0, sizeof(unsigned), d->stream));
+    d->stages_total = 0;
+    return do_init(d, INIT_BIAS, 0);
+}
+
 // Run nbits trellis stages on device-resident symbols.  Returns renormalisation count or -1.
 // Every launch carries the stage counter it was issued for; a kernel whose predecessor declined (saturation
 // watch) finds a different counter in the control block and declines too, so the host can enqueue a whole
@@ -208,6 +240,7 @@ TraceArgs trace_args(Decoder *d) { return TraceArgs{d->ring, d->row_fmt, d->len}
 int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1, int arg_s1 = -1)
 {
     if (nbits <= 0) return 0;
+    d->stages_total += nbits;
     const long long T_start = d->h_ctl->T;
     const int ren_start = d->h_ctl->renorm_count;
     constexpr int BATCH_STAGES = 8192;
@@ -286,6 +319,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
     const int fused_total = nbits / FK * FK;
     int pos = 0;
     bool lockstep = true;
+    for (int s = 0; s < nctx; s++) ds[s]->stages_total += nbits;
     for (int s = 0; s < nctx; s++) if (ds[s]->force_single || ds[s]->force_sat) lockstep = false;
     while (lockstep && pos < fused_total) {
         const int end = std::min(fused_total, pos + BATCH_STAGES);
@@ -328,6 +362,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         int r = 0;
         if (done < nbits) {
             // the decoder's own stream takes the rest; everything so far ran on d0's stream and is complete
+            d->stages_total -= nbits - done;           // update_core counts them itself
             r = update_core(d, dev_syms[s] + 2 * (size_t)done, nbits - done);
             if (r < 0) return -1;
         }
@@ -553,6 +588,19 @@ void *create_viterbi224(int len)
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
     if (cudaSetDevice(dev) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", dev); cudaGetLastError(); return nullptr; }
 
+    {
+        Decoder *r = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_dec_mu);
+            for (size_t i = 0; i < g_dec_pool.size(); i++)
+                if (g_dec_pool[i]->dev == dev && g_dec_pool[i]->len == len) { r = g_dec_pool[i]; g_dec_pool.erase(g_dec_pool.begin() + i); break; }
+        }
+        if (r) {
+            if (recycle(r) == 0) return r;
+            r->magic = MAGIC;
+            destroy(r);                                  // something is wrong with it: fall through to a fresh one
+        }
+    }
     Decoder *d = static_cast<Decoder *>(calloc(1, sizeof(Decoder)));
     if (!d) return nullptr;
     d->magic = MAGIC;
@@ -716,7 +764,21 @@ int min_metric_viterbi224(void *p) { return metric_extreme(p, 0); }
 void delete_viterbi224(void *p)
 {
     Decoder *d = as_dec(p);
-    if (d) destroy(d);
+    if (!d) return;
+    // the next create_viterbi224 of the same size gets this decoder back (decode.c:216-229 deletes and creates per frame)
+    for (int i = 0; i < MAX_CTX - 1; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
+    Decoder *evict = nullptr;
+    bool pooled = false;
+    if (d->ring_bytes <= POOL_MAX_BYTES / 2 && cudaSetDevice(d->dev) == cudaSuccess && cudaStreamSynchronize(d->stream) == cudaSuccess) {
+        d->magic = 0;                                    // a stale handle is rejected while the decoder waits in the pool
+        std::lock_guard<std::mutex> lk(g_dec_mu);
+        g_dec_pool.push_back(d);
+        pooled = true;
+        if (g_dec_pool.size() > DEC_POOL_MAX) { evict = g_dec_pool.front(); g_dec_pool.erase(g_dec_pool.begin()); }
+    }
+    cudaGetLastError();
+    if (evict) { evict->magic = MAGIC; destroy(evict); }
+    if (!pooled) destroy(d);
 }
 
 // ==========================================================================================

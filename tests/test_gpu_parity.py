@@ -123,6 +123,29 @@ def test_empty_and_degenerate_calls():
             assert np.array_equal(d.chainback(45, 9), o.chainback(45, 9))
 
 
+def test_recycled_decoder_is_indistinguishable_from_a_fresh_one(golden_cases):
+    """delete_viterbi224 parks the decoder, the next create_viterbi224 of the same size gets it back (decode.c:216-229
+    creates and deletes per frame): default options, zero counters, the rows it wrote read as zero, init(0) state --
+    and a golden script runs on it exactly as on a new one."""
+    syms = np.random.default_rng(3).integers(0, 256, 2 * 100, dtype=np.uint8)
+    d = v224.Viterbi224(72)
+    d.set_option("force_careful", 1)
+    d.init(0x1234)
+    d.update_blk(syms, 100)                              # wraps the 72-row ring
+    assert any(crc(d.get_row(k)) != crc(np.zeros(1 << 18, np.uint32)) for k in range(72))
+    d.delete()
+    with v224.Viterbi224(72) as r:
+        st = r.stats()
+        assert st["stages"] == 0 and st["fused_passes"] == 0 and st["launches"] <= 2 and st["renormals"] == 0, st
+        zero = crc(np.zeros(1 << 18, np.uint32))
+        assert all(crc(r.get_row(k)) == zero for k in range(72))
+        m = r.get_metrics()
+        assert m[0] == -32768 and m[1] == -32768 + 5000 and m[0x1234] == -32768 + 5000
+    case = golden_cases["saturation_forced_72"]
+    got = run_script(gpu_factory(), case["script"], case["syms"])      # the suite as a whole creates and deletes same-sized decoders all the time
+    compare_outcomes(got, case["outcome"], "recycled decoder vs golden")
+
+
 def test_block_stream_equals_per_bit_abi_loop():
     """v224x_stream_decode == the vdecode.c:145-152 loop through the nine-entry ABI (both on the GPU)."""
     bits, syms = S.telemetry_stream(700, 3.0, seed=41)
