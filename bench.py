@@ -252,9 +252,9 @@ def workload_config(n):
             "parallelism": (f"time-segmented x{n} GPUs, warm-up {WARMUP_STAGES} stages; " if n > 1 else "single GPU; ")
                            + f"per GPU {SEGMENTS} decoders in lockstep over contiguous segments, hand-overs verified on the device "
                              f"(warm-up {DELAY}+{CONV} stages each)",
-            "cache": "decision ring 8.2 GiB per GPU is written once per stage and is far larger than the 126 MB L2; the two 16 MiB "
-                     "path-metric buffers are re-read by the next pass by construction (no artificial L2 flush possible without "
-                     "changing the algorithm)"}
+            "cache": "the decision rings (8.2 GiB per decoder) are written once per stage and are far larger than the 126 MB L2; the "
+                     "16 MiB path-metric buffers (3 per decoder) are re-read by the next pass by construction (no artificial L2 "
+                     "flush possible without changing the algorithm)"}
 
 
 def main():
