@@ -200,7 +200,9 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t labe
 {
     uint32_t dw[NQ];
     acs_stage<T>(A, labels, tab, dw);
-    uint32_t *dst = ring_chunk + (size_t)tab[OPTAB_WORDS + T - 1] * ROWWORDS;
+    // row * 1 MiB + this thread's chunk: one 32 x 32 + 64 multiply-add
+    uint32_t *dst;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(dst) : "r"(tab[OPTAB_WORDS + T - 1]), "n"((unsigned)ROWBYTES), "l"(ring_chunk));
     if (NQ == 4) st_cs_v4(dst, make_uint4(dw[0], dw[1], dw[NQ - 2], dw[NQ - 1]));
     else         st_cs_v2(dst, dw[0], dw[1]);
     if (threadIdx.x == 0) s0[T] = A[0][0] & 0xffffu;               // slot 0 (tile 0, thread 0) always holds state 0
