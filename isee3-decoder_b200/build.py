@@ -31,7 +31,9 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-HOST_PROGRAMS = {"vdecode_block": os.path.join(HERE, "host", "vdecode_block.cpp")}
+HOST_PROGRAMS = {"vdecode_block": os.path.join(HERE, "host", "vdecode_block.cpp"),
+                 "decode_block": os.path.join(HERE, "host", "decode_block.cpp")}
+HOST_HEADERS = [os.path.join(HERE, "host", "hostfmt.h")]
 BIN = os.path.join(HERE, "bin")
 
 
@@ -41,7 +43,7 @@ def build_host_programs(force=False):
     outs = []
     for name, src in HOST_PROGRAMS.items():
         exe = os.path.join(BIN, name)
-        if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(LIB), *map(os.path.getmtime, HOST_HEADERS)):
             cmd = ["g++", "-O2", "-Wall", "-std=c++17", "-o", exe, src, "-L" + HERE, "-lviterbi224_b200", "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
@@ -73,7 +75,7 @@ def build_library(force=False, verbose=False, out=None, extra_flags=()):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(lib + ".ptxas.log" if variant else os.path.join(CSRC, "ptxas.log"), "w") as f:
-        f.write("\n".join(log))
+        f.write("\n".join(l for l in "\n".join(log).split("\n") if "Compile time" not in l))
     if variant:
         for o in objs:
             os.remove(o)

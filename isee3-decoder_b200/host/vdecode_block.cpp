@@ -15,6 +15,10 @@
 // Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 4),
 // -P  pairs only: write the symbol pairs that would go to the decoder (2 bytes each) to stdout and exit -- no GPU needed;
 // the CPU test tier checks the pairing / phase-flip logic through it.
+// -f  frames instead of bits: standard output is what `vdecode | framer` prints (framer.c:61-95: a 1024-bit shift
+// register over the decoded bits; whenever its last 40 bits are the sync word, a header line and the hex dump of the
+// frame), -r bitrate  for the frame time stamp (framer's option, default 512).  Saves the one-character-per-bit pipe.
+// -b  with -f: standard input already is decoded bits ('0'/'1' characters): only the framing runs -- a `framer`; no GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +27,7 @@
 #include <unistd.h>
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
+#include "hostfmt.h"
 
 namespace {
 
@@ -59,12 +64,12 @@ struct PairRec {
 
 int main(int argc, char *argv[])
 {
-    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4, pairs_only = 0;
+    int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4, pairs_only = 0, framing = 0, bitrate = 512, bits_in = 0;
     long block = 262144;
     const char *lang = getenv("LANG");
     setlocale(LC_ALL, lang ? lang : "en_US.utf8");                       // vdecode.c:59-62 (thousands separators in the status line)
     int opt;
-    while ((opt = getopt(argc, argv, "d:pi:qFB:S:P")) != -1) {
+    while ((opt = getopt(argc, argv, "d:pi:qFB:S:Pfr:b")) != -1) {
         switch (opt) {
         case 'F': dontflip = 1; break;
         case 'q': quiet = 1; break;
@@ -74,6 +79,9 @@ int main(int argc, char *argv[])
         case 'B': block = atol(optarg); break;
         case 'S': nseg = atoi(optarg); break;
         case 'P': pairs_only = 1; break;
+        case 'f': framing = 1; break;
+        case 'b': bits_in = 1; break;
+        case 'r': bitrate = atoi(optarg); break;
         default: break;
         }
     }
@@ -86,7 +94,7 @@ int main(int argc, char *argv[])
     if (block < 1024) block = 1024;
     const int ring_rows = delay + 8192;                                   // the library works through a block in chunks of (rows - delay)
     void *vd = nullptr;
-    if (!pairs_only) {
+    if (!pairs_only && !(framing && bits_in)) {
         vd = create_viterbi224(ring_rows);
         if (!vd) { fprintf(stderr, "%s: create_viterbi224 failed: %s\n", argv[0], v224x_last_error()); return 1; }
         init_viterbi224(vd, 0);                                           // vdecode.c:96
@@ -111,6 +119,33 @@ int main(int argc, char *argv[])
     // per-pair state of the output side (vdecode.c:147-184)
     int startup = delay;
     unsigned long long re_encoder = 0, symerrs = 0, nbits = 0;
+    // -f: framer.c's 1024-bit shift register (newest bit at the end), frame and bit counters
+    unsigned char shreg[128] = {0};
+    unsigned long long fr_frames = 1, fr_bits = 0, last40 = 0;
+    int shpos = 0;                       // the register is kept as a ring of bits: bit index of the oldest bit
+    auto frame_bit = [&](int bit) {
+        // overwrite the oldest bit with the newest (ring instead of shifting 1024 bits along, framer.c:66-72)
+        unsigned char &b = shreg[shpos >> 3];
+        const unsigned char m = (unsigned char)(0x80u >> (shpos & 7));
+        b = bit ? (b | m) : (b & ~m);
+        shpos = (shpos + 1) & 1023;
+        last40 = ((last40 << 1) | (unsigned long long)bit) & 0xffffffffffull;
+        if (last40 == SYNCWORD) {                                        // framer.c:74
+            printf("Frame %'llu at bit %'llu (%s)\n", fr_frames, fr_bits, v224host::format_hms((double)fr_bits / bitrate).c_str());
+            unsigned char fr[128];
+            for (int i = 0; i < 128; i++) {
+                // 8 bits starting at ring bit shpos + 8 i
+                const int p = (shpos + 8 * i) & 1023, sh = p & 7;
+                const unsigned hi = shreg[p >> 3], lo = shreg[((p >> 3) + 1) & 127];
+                fr[i] = (unsigned char)(((hi << 8 | lo) >> (8 - sh)) & 0xff);
+            }
+            v224host::print_frame_hex(stdout, fr, 128);
+            fr_frames++;
+            putchar('\n');
+            fflush(stdout);
+        }
+        fr_bits++;
+    };
 
     auto flush_block = [&]() -> int {
         const int n = (int)pairs.size();
@@ -139,7 +174,8 @@ int main(int argc, char *argv[])
             while (nf < flip_at.size() && flip_at[nf] == (size_t)i) { fprintf(stderr, "%s: flipping phase\n", argv[0]); nf++; }
             if (startup == 0) {
                 const int bit = bits[i];
-                outbuf.push_back(bit ? '1' : '0');
+                if (framing) frame_bit(bit);
+                else outbuf.push_back(bit ? '1' : '0');
                 re_encoder = (re_encoder << 1) | (unsigned long long)bit;
             } else {
                 startup--;
@@ -160,6 +196,14 @@ int main(int argc, char *argv[])
         return 0;
     };
 
+    if (framing && bits_in) {
+        for (;;) {
+            const size_t got = fread(inbuf.data(), 1, inbuf.size(), stdin);
+            if (got == 0) break;
+            for (size_t p = 0; p < got; p++) frame_bit(inbuf[p] == '1');      // framer.c:65: anything but '1' counts as 0
+        }
+        return 0;
+    }
     for (;;) {
         const size_t got = fread(inbuf.data(), 1, inbuf.size(), stdin);
         if (got == 0) break;

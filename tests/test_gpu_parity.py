@@ -7,6 +7,7 @@ Bar: bit-exact (integer arithmetic): decoded bytes, every decision row, every pa
 renormalisation counts and min/max metrics."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -286,6 +287,66 @@ def test_native_block_driver_prints_what_stock_vdecode_prints():
     assert a.stdout == b.stdout and len(a.stdout) > 46_000
     la, lb = _status_lines(a.stderr), _status_lines(b.stderr)
     assert la == lb and sum(b"flipping phase" in x for x in la) >= 2 and sum(b"symerrs" in x for x in la) >= 9, la
+
+
+def _strip_argv0(stdout_bytes):
+    """decode prints argv[0] in front of its banner lines; everything else is compared byte for byte."""
+    return [ln.split(b": ", 1)[1] if (b": Fano" in ln or b": Not displaying" in ln) else ln for ln in stdout_bytes.split(b"\n")]
+
+
+def test_frame_decoder_prints_what_stock_decode_prints():
+    """isee3-decoder_b200/bin/decode_block (frames of a locked run decoded side by side, speculatively, in one
+    v224x_decode_frames call) against `decode -V`:
+    (1) the output recorded from the UNMODIFIED reference (decode.c + viterbi224_sse2.c, tools/make_golden_host.py):
+        junk prefix, false first sync (bad frame), lock, 100 symbols lost (bad frame, re-acquisition), 5 symbols inserted;
+    (2) the same for 60 frames at 3 dB with four disturbances (56 frames, 5 bad);
+    (3) stock decode.c linked against our library on that stream, with and without -n, at several batch sizes."""
+    blk = os.path.join(ROOT, "isee3-decoder_b200", "bin", "decode_block")
+    assert os.path.exists(blk), "decode_block not built (python __graft_entry__.py build)"
+    env = dict(os.environ, LANG="C", V224_HOST_STATS="1")
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "host", "decode_V_seed21.npz"))
+    want = _strip_argv0(bytes(fx["stdout"]))
+    for extra in ([], ["-B", "1"], ["-B", "3", "-L", "2"]):
+        out = subprocess.run([blk, "-V"] + extra, input=fx["symbols"].tobytes(), capture_output=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stderr
+        assert _strip_argv0(out.stdout) == want, extra
+    assert sum(ln.startswith(b"Frame ") for ln in want) == 7 and sum(ln.endswith(b"(bad)") for ln in want) == 3
+    # (2) 60 frames at 3 dB, symbols cut (40, 1000) and inserted (7, 300) inside four different frames, truncated end:
+    #     the UNMODIFIED reference printed 56 frames, 5 of them bad (fixture; ~2.5 min of CPU when it was recorded)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import zlib
+    import make_golden_host
+    soft = make_golden_host.decode_stream_long()
+    fxl = np.load(os.path.join(ROOT, "tests", "golden", "host", "decode_V_long_seed77.npz"))
+    assert zlib.crc32(soft.tobytes()) == int(fxl["symbols_crc"]), "stream generator drifted from the fixture"
+    out = subprocess.run([blk, "-V"], input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    assert _strip_argv0(out.stdout) == _strip_argv0(bytes(fxl["stdout"]))
+    assert out.stdout.count(b"Frame ") == 56 and out.stdout.count(b"(bad)") == 5
+    # (3) the same stream through stock decode.c linked against our library, with and without -n, at another batch size
+    for flags in (["-V"], ["-V", "-n", "-r", "2048"]):
+        a = subprocess.run([_bin("decode_b200")] + flags, input=soft.tobytes(), capture_output=True, timeout=900, env=env)
+        assert a.returncode == 0, a.stderr[-300:]
+        for extra in ([], ["-B", "5"]):
+            b = subprocess.run([blk] + flags + extra, input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+            assert b.returncode == 0, b.stderr[-300:]
+            assert _strip_argv0(a.stdout) == _strip_argv0(b.stdout), (flags, extra)
+        assert a.stdout.count(b"Frame ") == (51 if "-n" in flags else 56)
+    assert b"speculative frames discarded" in b.stderr
+
+
+def test_framing_mode_equals_the_vdecode_framer_pipeline():
+    """vdecode_block -f prints what `vdecode | framer` prints (framer.c:61-95): here vdecode_block's own bit stream piped
+    through the unmodified reference framer (oracle/_ref/framer_ref), on a stream with a phase flip."""
+    blk = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    env = dict(os.environ, LANG="C")
+    _, soft = S.telemetry_stream(24 * 1024, 3.0, seed=14, junk_symbols=55)
+    bits = subprocess.run([blk, "-d", "200", "-q"], input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+    assert bits.returncode == 0, bits.stderr
+    want = subprocess.run([_bin("framer_ref"), "-r", "512"], input=bits.stdout, capture_output=True, timeout=60, env=env)
+    got = subprocess.run([blk, "-d", "200", "-q", "-f", "-r", "512", "-B", "7000"], input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+    assert got.returncode == 0, got.stderr
+    assert got.stdout == want.stdout and got.stdout.count(b"Frame ") >= 20
 
 
 # ---------------------------------------------------------------------------------------------

@@ -133,3 +133,56 @@ def test_block_driver_pairing_equals_the_python_mirror(built):
         assert got.shape == want.shape and np.array_equal(got, want), args
     r = subprocess.run([exe, "-P"], input=soft.tobytes(), capture_output=True, timeout=120)
     assert r.stderr.count(b"flipping phase") == len(v224.vdecode.pair_symbols(soft, return_flips=True)[1]) >= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# the "next" rows of the scope table: framer and the frame decoder's sync search (host side, no GPU)
+# ---------------------------------------------------------------------------------------------
+def _host_golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", "host", name + ".npz"))
+
+
+def test_framer_mode_prints_what_the_reference_framer_prints(built):
+    """vdecode_block -f -b (framing only) against the recorded output of the unmodified framer.c (tools/make_golden_host.py):
+    junk prefix, five good frames, one frame whose sync word carries a bit error (not reported)."""
+    fx = _host_golden("framer_seed7")
+    bits = np.unpackbits(fx["bits"])[: int(fx["nbits"])]
+    txt = bytes(np.where(bits == 1, ord("1"), ord("0")).astype(np.uint8))
+    exe = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    r = subprocess.run([exe, "-f", "-b", "-r", "512"], input=txt, capture_output=True, timeout=60, env=dict(os.environ, LANG="C"))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == bytes(fx["stdout"]) and r.stdout.count(b"Frame ") == 5
+
+
+def frame_sync_literal(soft):
+    """decode.c:152-192,270-282 with lock never asserted: per frame, first arg-max of the 34-tap correlator over 2048
+    positions, then skip sync_start + 2048 symbols (test-side restatement)."""
+    taps = np.where(S.sync_vector() == 1, 1, -1).astype(np.int64)
+    x = soft.astype(np.int64) - 128
+    base, out = 0, []
+    while base + 2048 + 34 <= x.size:
+        corr = np.correlate(x[base: base + 2048 + 33], taps, mode="valid")      # corr[i] = sum_k x[base+i+k] * taps[k]
+        ss = int(np.argmax(corr[:2048]))
+        if base + ss + 2048 + 34 > x.size:
+            break
+        out.append(base + ss + 34)
+        base += ss + 2048
+    return out
+
+
+def test_frame_decoder_sync_search_equals_the_literal_loop(built):
+    """decode_block -S (sync search only, no GPU) on the stream of the decode golden fixture and on a noisier one; the
+    positions of the good frames are the ones the unmodified decode.c printed."""
+    exe = os.path.join(ROOT, "isee3-decoder_b200", "bin", "decode_block")
+    fx = _host_golden("decode_V_seed21")
+    _, noisy = S.telemetry_stream(12 * 1024, 1.0, seed=33, junk_symbols=4001)
+    for soft in (fx["symbols"], noisy):
+        r = subprocess.run([exe, "-S"], input=soft.tobytes(), capture_output=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        got = [int(x) for x in r.stdout.split()]
+        assert got == frame_sync_literal(soft) and len(got) >= 6
+    # the reference's own printout: every frame it found by searching (the first, and each one after a bad frame) is in the list
+    ref_lines = [ln for ln in bytes(fx["stdout"]).decode().splitlines() if ln.startswith("Frame ")]
+    r = subprocess.run([exe, "-S"], input=fx["symbols"].tobytes(), capture_output=True, timeout=60)
+    found = set(int(x) for x in r.stdout.split())
+    assert int(ref_lines[0].split()[4]) in found

@@ -19,3 +19,4 @@ build() { # name, sources...
 build vtest224_b200   $REF/vtest224.c $REF/encode.c $REF/sim.c
 build vdecode_b200    $REF/vdecode.c $REF/timeformat.c
 build hybridtest_b200 $REF/hybridtest.c $REF/encode.c $REF/fano.c $REF/metrics.c $REF/sim.c
+build decode_b200     $REF/decode.c $REF/timeformat.c $REF/metrics.c $REF/fano.c
