@@ -31,6 +31,7 @@ WARM = 2048
 CONV = 2048
 SEGMENTS = 3
 SEED = 50505
+GEN_BLOCK = 1 << 24     # the stream's generation unit (bits)
 K = 24
 POLY1 = 0o73665667
 POLY2 = 0o73665665
@@ -108,22 +109,30 @@ def main():
         torch.cuda.synchronize()
 
     per = args.bits // world
-    assert per * world == args.bits and per > 4 * (WARM + DELAY), "bits must divide by the number of GPUs"
-    # this rank's data bits, plus the tail of the previous rank's (warm-up + encoder history)
+    assert per * world == args.bits and per % GEN_BLOCK == 0, f"bits per GPU must be a multiple of {GEN_BLOCK}"
+    # The stream is defined in blocks of GEN_BLOCK bits keyed by (seed, block index) -- data and noise -- so that its bytes
+    # do not depend on the number of GPUs: runs at different N decode the SAME stream and their outputs can be compared.
     t_gen = time.perf_counter()
-    bits = gen_bits(torch, dev, SEED, rank, per)
+
+    def block(j):
+        bits_j = gen_bits(torch, dev, SEED, j, GEN_BLOCK)
+        hist = gen_bits(torch, dev, SEED, j - 1, GEN_BLOCK)[-(K - 1):].clone() if j > 0 else torch.zeros(K - 1, dtype=torch.uint8, device=dev)
+        s1, s2 = encode(torch, hist, bits_j)
+        return bits_j, soften(torch, s1, s2, args.ebn0, SEED, j)
+
+    first = rank * per // GEN_BLOCK
+    parts = [block(j) for j in range(first, first + per // GEN_BLOCK)]
     if rank == 0:
-        lead = torch.zeros(0, dtype=torch.uint8, device=dev)
-        hist = torch.zeros(K - 1, dtype=torch.uint8, device=dev)
+        lead_bits = torch.zeros(0, dtype=torch.uint8, device=dev)
+        lead_soft = torch.zeros(0, dtype=torch.uint8, device=dev)
     else:
-        prev = gen_bits(torch, dev, SEED, rank - 1, per)
-        lead = prev[-WARM:].clone()
-        hist = prev[-WARM - (K - 1):-WARM].clone()
-        del prev
-    data = torch.cat([lead, bits])
-    s1, s2 = encode(torch, hist, data)
-    soft = soften(torch, s1, s2, args.ebn0, SEED, rank)
-    del s1, s2
+        pb, ps = block(first - 1)
+        lead_bits, lead_soft = pb[-WARM:].clone(), ps[-2 * WARM:].clone()
+        del pb, ps
+    lead = lead_bits
+    data = torch.cat([lead_bits] + [p[0] for p in parts])
+    soft = torch.cat([lead_soft] + [p[1] for p in parts])
+    del parts
     n = data.numel()
     out = torch.zeros(n, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
@@ -159,18 +168,28 @@ def main():
     skip = lead.numel() if rank else LAG
     got = out[skip:]
     want = data[skip - LAG: n - LAG]
-    errs = int((got != want).sum().item())
+    wrong = torch.nonzero(got != want).flatten()
+    errs = int(wrong.numel())
     checked = int(got.numel())
+    # absolute data-bit positions of the errors (at most 512 per rank), gathered on rank 0
+    pos = torch.full((512,), -1, dtype=torch.int64, device=dev)
+    k = min(512, errs)
+    pos[:k] = wrong[:k] + (skip - LAG) + (rank * per - lead.numel())
+    near_start = int((wrong < 8192).sum().item()) if rank else 0           # errors right behind a rank's warm-up
 
     t = torch.tensor([ms, wall * 1e3, t_gen * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(errs), float(checked), float(st["launches"] - l0["launches"]), float(rep.get("redone", 0)),
-                        float(rep.get("extra_stages", 0) + (lead.numel()))], dtype=torch.float64, device=dev)
+                        float(rep.get("extra_stages", 0) + (lead.numel())), float(near_start)], dtype=torch.float64, device=dev)
+    allpos = [pos]
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        allpos = [torch.zeros_like(pos) for _ in range(world)]
+        dist.all_gather(allpos, pos)
     if rank == 0:
         ms_max, wall_max, gen_max = (float(x) for x in t)
-        errs_t, checked_t, launches_t, redone_t, extra_t = (float(x) for x in tot)
+        errs_t, checked_t, launches_t, redone_t, extra_t, near_t = (float(x) for x in tot)
+        positions = sorted(int(x) for x in torch.cat(allpos).tolist() if x >= 0)
         value = args.bits / (ms_max * 1e-3)
         print(json.dumps({
             "config": "BASELINE config 5: box-scale throughput sweep, time-segmented",
@@ -181,6 +200,7 @@ def main():
             "handovers_verified_rank0": rep.get("verified"), "segments_redone_all_ranks": int(redone_t),
             "extra_stages_all_ranks": int(extra_t), "overhead_frac": extra_t / args.bits,
             "bit_errors_vs_transmitted": int(errs_t), "bits_checked": int(checked_t), "ber": errs_t / max(1.0, checked_t),
+            "bit_errors_within_8192_bits_of_a_rank_start": int(near_t), "error_positions": positions,
             "prefix_1M_segmented_identical_to_sequential_rank0": prefix_same, "gpu_launches": int(launches_t),
             "passes_rank0": {k: st[k] - l0[k] for k in ("fused_passes", "careful_passes", "single_stages", "sat_stages")},
             "state_sharded_variant": "not kept: exchange floor 23.4 us/pass at G=8, 31.7 us at G=2 (profiles/r01_sharded_exchange_floor.jsonl)"}),

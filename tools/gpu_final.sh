@@ -8,5 +8,6 @@ timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 timeout 120 python tools/prof_multi.py default 3 2048 > gpurun_out/prof_multi_plain.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_acs_persist -s 1 -c 1 -o gpurun_out/prof_final_3dec python tools/prof_multi.py default 3 2048 > gpurun_out/ncu_full.log 2>&1
+timeout 200 python tools/time_decode_block.py 1024 > gpurun_out/time_decode_block.log 2>&1; cat gpurun_out/time_decode_block.log
 cat gpurun_out/prof_multi_plain.log; tail -2 gpurun_out/ncu_full.log; wc -l gpurun_out/launches.csv
 cut -c1-400 gpurun_out/bench.log
