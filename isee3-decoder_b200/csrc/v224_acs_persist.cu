@@ -112,6 +112,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
                  ::"r"(smem_addr(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+// The protocol warps' waits last about as long as a tile's compute time, and the try_wait loop above comes round every
+// ~35 ns (ncu source page: 300-400 iterations per tile, 23 % of all instructions the kernel issues).  Polling with a real
+// sleep in between was measured as an alternative (V224_PROTO_SLEEP_NS = 100 .. 1600): no gain with 3 decoders in lockstep
+// (8.94 - 9.16 vs 9.01 us per pass), 1 - 8 % slower with one -- the spin fills issue slots nobody else wants, the compute
+// rounds are bound by the ALU/FMA pipes (profiles/r01_ab_proto_sleep.txt).  Default 0 = the hardware wait.
+#ifndef V224_PROTO_SLEEP_NS
+#define V224_PROTO_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_proto(uint64_t *bar, unsigned parity)
+{
+#if V224_PROTO_SLEEP_NS > 0
+    while (!mbar_test(bar, parity)) __nanosleep(V224_PROTO_SLEEP_NS);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
 {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
@@ -456,8 +472,8 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
     const unsigned per_pass = (unsigned)m.nctx * FUSED_TILES;
     for (unsigned k = 0;; k++) {
         const unsigned b = k % NSLOT;
-        if (k >= (unsigned)NSLOT) mbar_wait(&sm.slotfree[b], (k / NSLOT - 1) & 1);       // tile k - NSLOT is done with the slot
-        if (BULK_LOAD && k >= 2) mbar_wait(&sm.freeb[k & 1], ((k - 2) >> 1) & 1);      // tile k - 2 has read the data buffer
+        if (k >= (unsigned)NSLOT) mbar_wait_proto(&sm.slotfree[b], (k / NSLOT - 1) & 1);       // tile k - NSLOT is done with the slot
+        if (BULK_LOAD && k >= 2) mbar_wait_proto(&sm.freeb[k & 1], ((k - 2) >> 1) & 1);      // tile k - 2 has read the data buffer
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(queue, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -540,12 +556,12 @@ __device__ void retirer_warp(FusedSmem &sm, const MultiArgs &m)
     const unsigned lane = threadIdx.x & 31;
     for (unsigned k = 0;; k++) {
         const unsigned b = k % NSLOT, par = (k / NSLOT) & 1;
-        mbar_wait(&sm.full[b], par);
+        mbar_wait_proto(&sm.full[b], par);
         const TileInfo &ti = sm.info[b];
         const int go = ti.go, n = ti.n, s = ti.s;
         const unsigned tau = ti.tau;
         if (go < 0) return;
-        mbar_wait(&sm.done[b], par);               // every compute warp has issued the tile's stores and is done with the slot
+        mbar_wait_proto(&sm.done[b], par);         // every compute warp has issued the tile's stores and is done with the slot
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.slotfree[b]);
         if (go > 0 && lane == 0) {

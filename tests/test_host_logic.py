@@ -186,3 +186,23 @@ def test_frame_decoder_sync_search_equals_the_literal_loop(built):
     r = subprocess.run([exe, "-S"], input=fx["symbols"].tobytes(), capture_output=True, timeout=60)
     found = set(int(x) for x in r.stdout.split())
     assert int(ref_lines[0].split()[4]) in found
+
+
+def test_config5_stream_generator_matches_the_reference_encoder_mirror():
+    """tools/config5.py builds its stream with torch ops (on the GPU in the real run): its encoder must be the encoder of
+    encode.c:17-35 (numpy mirror in streams.py, itself pinned by the golden fixtures), including the carried-over history,
+    and its quantiser must produce symdemod-format bytes."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config5
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, 5000, dtype=np.uint8)
+    state = int(rng.integers(0, 1 << 23))
+    hist = np.array([(state >> i) & 1 for i in range(22, -1, -1)], dtype=np.uint8)          # oldest first
+    s1, s2 = config5.encode(torch, torch.from_numpy(hist), torch.from_numpy(bits))
+    want, _ = S.encode_bits(bits, state)
+    assert np.array_equal(s1.numpy(), want[0::2]) and np.array_equal(s2.numpy(), want[1::2])
+    soft = config5.soften(torch, s1, s2, 60.0, 1, 0).numpy()                                  # noiseless: 128 +- amplitude, clipped
+    a, _ = S.symdemod_amplitudes(60.0)
+    lo, hi = int(np.clip(128.0 - a, 0, 255)), int(np.clip(128.0 + a, 0, 255))
+    assert set(np.unique(soft).tolist()) <= {lo - 1, lo, lo + 1, hi - 1, hi, hi + 1} and np.array_equal(soft > 128, want.astype(bool))
