@@ -33,7 +33,7 @@ def is_stale():
 
 HOST_PROGRAMS = {"vdecode_block": os.path.join(HERE, "host", "vdecode_block.cpp"),
                  "decode_block": os.path.join(HERE, "host", "decode_block.cpp")}
-HOST_HEADERS = [os.path.join(HERE, "host", "hostfmt.h")]
+HOST_HEADERS = [os.path.join(HERE, "host", "hostfmt.h"), os.path.join(HERE, "host", "fano_seq.h")]
 BIN = os.path.join(HERE, "bin")
 
 

@@ -335,6 +335,35 @@ def test_frame_decoder_prints_what_stock_decode_prints():
     assert b"speculative frames discarded" in b.stderr
 
 
+def test_frame_decoder_fano_first_mode_prints_what_stock_decode_prints():
+    """decode_block in the reference's default mode -- Fano on the host first, the frames it gives up on decoded by the GPU
+    in one batch per run -- against the printouts recorded from the UNMODIFIED reference (`decode`, `decode -p -n`;
+    tools/make_golden_host.py): which decoder each frame is credited to, partial Fano output of frames that were not
+    retried, lock losses; and against stock decode.c on our library for a longer stream."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import zlib
+    import make_golden_host
+    blk = os.path.join(ROOT, "isee3-decoder_b200", "bin", "decode_block")
+    env = dict(os.environ, LANG="C", V224_HOST_STATS="1")
+    n_viterbi = 0
+    for name, flags, soft in make_golden_host.hybrid_cases():
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "host", name + ".npz"))
+        assert zlib.crc32(soft.tobytes()) == int(fx["symbols_crc"]), "stream generator drifted from the fixture"
+        for extra in ([], ["-B", "3"]):
+            out = subprocess.run([blk] + flags + extra, input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+            assert out.returncode == 0, out.stderr
+            assert _strip_argv0(out.stdout) == _strip_argv0(bytes(fx["stdout"])), (name, extra)
+        n_viterbi += out.stdout.count(b"with Viterbi")
+    assert n_viterbi >= 20
+    _, soft = S.telemetry_stream(120 * 1024, 1.9, seed=31, junk_symbols=700)
+    for flags in ([], ["-p"]):
+        a = subprocess.run([_bin("decode_b200")] + flags, input=soft.tobytes(), capture_output=True, timeout=900, env=env)
+        b = subprocess.run([blk] + flags, input=soft.tobytes(), capture_output=True, timeout=300, env=env)
+        assert a.returncode == 0 and b.returncode == 0, (a.stderr[-300:], b.stderr[-300:])
+        assert _strip_argv0(a.stdout) == _strip_argv0(b.stdout), flags
+        assert a.stdout.count(b"with Viterbi") >= 3 and a.stdout.count(b"with Fano") >= 80
+
+
 def test_framing_mode_equals_the_vdecode_framer_pipeline():
     """vdecode_block -f prints what `vdecode | framer` prints (framer.c:61-95): here vdecode_block's own bit stream piped
     through the unmodified reference framer (oracle/_ref/framer_ref), on a stream with a phase flip."""
