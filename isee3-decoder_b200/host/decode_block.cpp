@@ -31,6 +31,7 @@
 #include <cmath>
 #include <clocale>
 #include <vector>
+#include <chrono>
 #include <unistd.h>
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
@@ -155,6 +156,10 @@ int main(int argc, char *argv[])
         printf("%s: Specify only one of -F or -V\n", argv[0]);           // decode.c:117-120
         return 1;
     }
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const clk::time_point t_start = clk::now();
+    double t_create = 0, t_gpu = 0, t_fano = 0;
     int mettab[2][256];
     v224host::FanoDecoder fano;
     void *vd = nullptr;
@@ -170,7 +175,9 @@ int main(int argc, char *argv[])
     if (viterbi_enabled && !fano_enabled) {
         // Viterbi only: the decoder is needed from the first frame on (decode.c:138-147); with Fano first it is created
         // when the first frame falls through to it
+        const clk::time_point t0 = clk::now();
         vd = create_viterbi224(FRAMEBITS);
+        t_create += secs(t0, clk::now());
         if (!vd) {
             printf("%s: cannot set up the Viterbi decoder: %s\n", argv[0], v224x_last_error());
             return 2;
@@ -200,10 +207,12 @@ int main(int argc, char *argv[])
 
         // 1. Fano on the host for every frame of the run (decode.c:196-204; the cycle limit it passes is the constant 100)
         if (fano_enabled) {
+            const clk::time_point t0 = clk::now();
             memset(fano_data.data(), 0, (size_t)nb * FB);
             for (int f = 0; f < nb; f++)
                 fano_bits[f] = fano.decode(&fano_data[(size_t)f * FB], in.at(first + (unsigned long long)f * FRAMESYMBOLS), FRAMEBITS, mettab,
                                            fano_delta, 100, syncstate, syncstate).bits;
+            t_fano += secs(t0, clk::now());
         }
         // 2. the frames the reference would hand to the Viterbi decoder if every earlier frame of the run locks
         //    (decode.c:205-231): all of them without Fano; with Fano those it gave up on, frame 0 only if the previous
@@ -215,7 +224,9 @@ int main(int argc, char *argv[])
             if (viterbi_enabled && (!fano_enabled || ((persistent || prev_lock) && fano_bits[f] != FRAMEBITS))) vit_slot[f] = nv++;
         }
         if (nv) {
-            if (!vd && !(vd = create_viterbi224(FRAMEBITS))) {
+            const clk::time_point t0 = clk::now();
+            if (!vd) { vd = create_viterbi224(FRAMEBITS); t_create += secs(t0, clk::now()); }
+            if (!vd) {
                 // (the reference prints a notice and goes on with Fano's result, decode.c:212-215)
                 printf("%s: cannot set up the Viterbi decoder: %s\n", argv[0], v224x_last_error());
                 for (int f = 0; f < nb; f++) vit_slot[f] = -1;
@@ -230,10 +241,12 @@ int main(int argc, char *argv[])
                     if (vit_slot[f] >= 0) memcpy(&vit_syms[(size_t)vit_slot[f] * FRAMESYMBOLS], in.at(first + (unsigned long long)f * FRAMESYMBOLS), FRAMESYMBOLS);
                 src = vit_syms.data();
             }
+            const clk::time_point t0 = clk::now();
             if (v224x_decode_frames(vd, src, nv, FRAMEBITS, states.data(), states.data(), vit_data.data(), nlock) < 0) {
                 fprintf(stderr, "%s: decode failed: %s\n", argv[0], v224x_last_error());
                 return 1;
             }
+            t_gpu += secs(t0, clk::now());
             launches++;
         }
         // 3. replay the reference's per-frame logic in order
@@ -271,7 +284,8 @@ int main(int argc, char *argv[])
     }
     if (vd) delete_viterbi224(vd);
     if (getenv("V224_HOST_STATS"))
-        fprintf(stderr, "%s: %llu frames (%llu by Fano, %llu by Viterbi), %llu launches, %llu speculative frames discarded\n", argv[0], frames - 1,
-                n_fano_ok, n_viterbi, launches, wasted);
+        fprintf(stderr, "%s: %llu frames (%llu by Fano, %llu by Viterbi), %llu launches, %llu speculative frames discarded; "
+                "seconds: total %.2f, create %.2f, decode_frames %.2f, fano %.2f\n", argv[0], frames - 1,
+                n_fano_ok, n_viterbi, launches, wasted, secs(t_start, clk::now()), t_create, t_gpu, t_fano);
     return 0;
 }
