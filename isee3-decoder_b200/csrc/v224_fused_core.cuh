@@ -193,22 +193,14 @@ V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *o
             const uint32_t s0 = f_prmt(D0[2 * qq], D0[2 * qq + 1], 0xfdb9);
             const uint32_t s1 = f_prmt(D1[2 * qq], D1[2 * qq + 1], 0xfdb9);
             // bit 15 of D is the INVERTED decision; it is stored as it is (fused rows hold complemented bits, the
-            // traceback kernels flip them back: FUSED_ROWS_COMPLEMENTED) -- one LOP3 per 4 decisions, no final XOR
-#ifdef V224_GATHER_IMAD
-            // s = 255 * (one decision bit per byte): sum_i s_i * 2^i = 255 * (decision word) mod 2^32 -- the merge is a
-            // multiply-add on the FMA pipe instead of a LOP3 on the (busier) ALU pipe; one multiply by 255^-1 at the end
-            if (pidx == 0) { dw[qq] = s0; dw[NQ / 2 + qq] = s1; }
-            else { dw[qq] = s0 * (1u << pidx) + dw[qq]; dw[NQ / 2 + qq] = s1 * (1u << pidx) + dw[NQ / 2 + qq]; }
-#else
+            // traceback kernels flip them back: FUSED_ROWS_COMPLEMENTED) -- one LOP3 per 4 decisions, no final XOR.
+            // (Measured and dropped, profiles/r01_ab_imad_gather.txt, r01_ab_tree_gather.txt: merging with multiply-adds on
+            // the FMA pipe, and merging the eight 0x00/0xff words pairwise with bit-selects -- 7 instead of 8 LOP3 -- are
+            // both exact and both 1-2 % slower.)
             dw[qq] = (s0 & (0x01010101u << pidx)) | dw[qq];
             dw[NQ / 2 + qq] = (s1 & (0x01010101u << pidx)) | dw[NQ / 2 + qq];
-#endif
         }
     }
-#ifdef V224_GATHER_IMAD
-#pragma unroll
-    for (int w = 0; w < NQ; w++) dw[w] *= 0xFEFEFEFFu;       // 255 * 0xFEFEFEFF = 1 mod 2^32
-#endif
 }
 
 // packed min / max over a thread's 64 registers
