@@ -556,12 +556,16 @@ int frames_core(Decoder *d, const uint8_t *host_syms, int nframes, int framebits
         CU(cudaStreamSynchronize(st));
         d->launches += nb;
         if (multi_update_core(D, sp, nb, framebits, nullptr)) return -1;
+        // The group's tracebacks are independent chains of dependent ring loads (latency, not bandwidth): each runs on its
+        // own decoder's stream so that they overlap instead of queueing behind one another (the update above has completed:
+        // multi_update_core ends with a synchronisation).  All are through before the next group re-uses the rings.
         for (int i = 0; i < nb; i++) {
             const uint32_t es = end_states ? end_states[f0 + i] : 0u;
             CU(launch_chainback(trace_args(D[i]), (uint32_t)framebits, es, L, d->chain_warm, d->dout + fbytes * (size_t)(f0 + i), D[i]->seg, D[i]->seg + nseg,
-                                D[i]->d_redo, st));
+                                D[i]->d_redo, D[i]->stream));
             d->launches += 2;
         }
+        for (int i = 1; i < nb; i++) CU(cudaStreamSynchronize(D[i]->stream));
     }
     CU(cudaMemcpyAsync(host_data, d->dout, fbytes * (size_t)nframes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
