@@ -286,3 +286,34 @@ def test_frame_decoder_fano_only_mode_prints_what_the_reference_prints(built):
         bad += a.stdout.count(b"(bad)")
         good += a.stdout.count(b"Frame ") - a.stdout.count(b"(bad)")
     assert bad >= 20 and good >= 60, (bad, good)
+
+
+def test_host_programs_on_empty_short_and_ragged_input(built):
+    """Edge cases of the host programs that need no GPU: empty input, less than one frame, a stream that ends inside a
+    frame, sync words back to back and overlapping the stream start; framer mode against the unmodified framer where
+    oracle/_ref travelled."""
+    vb = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    db = os.path.join(ROOT, "isee3-decoder_b200", "bin", "decode_block")
+    env = dict(os.environ, LANG="C")
+    for cmd in ([vb, "-f", "-b"], [db, "-S"], [vb, "-P", "-q"]):
+        r = subprocess.run(cmd, input=b"", capture_output=True, timeout=60, env=env)
+        assert r.returncode == 0 and r.stdout == b"", cmd
+    r = subprocess.run([db, "-F"], input=b"", capture_output=True, timeout=60, env=env)
+    assert r.returncode == 0 and r.stdout.count(b"\n") == 2 and b"Frame" not in r.stdout          # the two banner lines only
+    _, soft = S.telemetry_stream(3 * 1024, 5.0, seed=8)
+    for n in (1, 2081, 2082, 4000, soft.size - 1):                       # 2082 = one frame + sync: the least the search needs (decode.c:152-161)
+        r = subprocess.run([db, "-S"], input=soft[:n].tobytes(), capture_output=True, timeout=60, env=env)
+        assert r.returncode == 0 and [int(x) for x in r.stdout.split()] == frame_sync_literal(soft[:n]), n
+    ref = os.path.join(ROOT, "oracle", "_ref", "framer_ref")
+    sync = [(S.SYNCWORD >> (39 - i)) & 1 for i in range(40)]
+    rng = np.random.default_rng(5)
+    cases = [sync, sync + sync, [0] * 7 + sync + [1] + sync, sync[1:] + sync, list(rng.integers(0, 2, 1500)) + sync + list(rng.integers(0, 2, 1024 - 40)) + sync]
+    for bits in cases:
+        txt = bytes(ord("1") if b else ord("0") for b in bits)
+        got = subprocess.run([vb, "-f", "-b"], input=txt, capture_output=True, timeout=60, env=env)
+        assert got.returncode == 0
+        nfr = got.stdout.count(b"Frame ")
+        assert nfr >= 1 and got.stdout.count(b"\n") == nfr * 10          # header + 8 hex lines + blank line per frame
+        if os.path.exists(ref):
+            want = subprocess.run([ref], input=txt, capture_output=True, timeout=60, env=env)
+            assert got.stdout == want.stdout, bits[:50]
