@@ -73,6 +73,8 @@ int v224x_stream_decode_seg_dev(void *p, const unsigned char *dev_syms, int nbit
  *     chainback_viterbi224(p, data_out + ceil(framebits/8)*f, framebits, end_states[f]);
  * (vtest224.c:116-118, hybridtest.c:186-193, decode.c:220-222), with up to nlock (1..4, <= 0: 4) frames side by side in
  * one persistent launch.  start_states / end_states may be NULL (all 0).  Needs framebits <= the handle's len.
+ * The tracebacks of a group run concurrently (one stream per decoder) and overlap the next group's ACS passes, which use a
+ * second set of decoders; the library owns up to 2 * nlock - 1 extra decoders of the handle's size for this.
  * Afterwards the handle holds the state of the last frame of its lane (as after that frame's chainback).
  * Returns 0, -1 on error. */
 int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int framebits, const unsigned int *start_states,

@@ -118,7 +118,7 @@ struct Decoder {
     uint32_t cache_end;
     unsigned *d_walk_steps;    // dependent loads spent in decodebit walks (test / tuning counter)
     // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
-    struct Decoder *aux[MAX_CTX - 1];
+    struct Decoder *aux[2 * MAX_CTX - 1];   // [0, MAX_CTX-1): lockstep partners of this decoder; [MAX_CTX-1, ..): second lane set of the frame batches
     uint16_t *snap;
     int *d_segdiff;            // [2 * MAX_CTX]: min / max of the metric difference at each hand-over check
     cudaEvent_t ev0, ev1, kev0, kev1;
@@ -131,6 +131,7 @@ struct Decoder {
     int time_kernels;
 };
 constexpr uint32_t MAGIC = 0x56323234u;   // "V224"
+constexpr int NAUX = 2 * MAX_CTX - 1;
 
 Decoder *as_dec(void *p)
 {
@@ -175,7 +176,7 @@ constexpr size_t DEC_POOL_MAX = 2;
 void destroy(Decoder *d)
 {
     if (!d) return;
-    for (int i = 0; i < MAX_CTX - 1; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
+    for (int i = 0; i < NAUX; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
     cudaSetDevice(d->dev);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
@@ -403,7 +404,7 @@ void swap_bodies(Decoder *d, Decoder *o)
     Decoder td = *d, to = *o;
     *d = to;
     *o = td;
-    for (int i = 0; i < MAX_CTX - 1; i++) { d->aux[i] = td.aux[i]; o->aux[i] = nullptr; }
+    for (int i = 0; i < NAUX; i++) { d->aux[i] = td.aux[i]; o->aux[i] = nullptr; }
     d->d_segdiff = td.d_segdiff; o->d_segdiff = to.d_segdiff;
     // streams and events stay with the handle too (a timer started on the handle must stop on the same events)
     d->stream = td.stream; o->stream = to.stream;
@@ -527,11 +528,21 @@ int frames_core(Decoder *d, const uint8_t *host_syms, int nframes, int framebits
     if (framebits <= 0 || framebits > d->len) { set_err("frame decode needs 0 < framebits <= len (framebits %d, len %d)", framebits, d->len); return -1; }
     const int S = std::max(1, std::min(std::min(nlock, MAX_CTX), nframes));
     const size_t fsyms = 2 * (size_t)framebits, fbytes = ((size_t)framebits + 7) / 8;
-    Decoder *D[MAX_CTX] = {d};
+    // Two lane sets: while one set's frames are in their traceback (latency-bound chains of dependent ring loads, each on
+    // its own decoder's stream) the other set's frames run their ACS passes.  Set 0 = this decoder + its lockstep partners,
+    // set 1 = S more decoders (only when there is a second group of frames).
+    const int nsets = nframes > S ? 2 : 1;
+    Decoder *D[2][MAX_CTX] = {{d}, {nullptr}};
     for (int i = 1; i < S; i++) {
         if (!d->aux[i - 1]) d->aux[i - 1] = make_aux(d);
-        D[i] = d->aux[i - 1];
-        if (!D[i]) { set_err("frame decode: cannot create decoder %d of %d: %s", i, S, g_err); return -1; }
+        D[0][i] = d->aux[i - 1];
+        if (!D[0][i]) { set_err("frame decode: cannot create decoder %d of %d: %s", i, S, g_err); return -1; }
+    }
+    for (int i = 0; nsets == 2 && i < S; i++) {
+        Decoder *&a = d->aux[MAX_CTX - 1 + i];
+        if (!a) a = make_aux(d);
+        D[1][i] = a;
+        if (!a) { set_err("frame decode: cannot create decoder %d of the second lane set: %s", i, g_err); return -1; }
     }
     if (grow((void **)&d->dsyms, &d->dsyms_cap, fsyms * (size_t)nframes)) return -1;
     if (grow((void **)&d->dout, &d->dout_cap, fbytes * (size_t)nframes)) return -1;
@@ -539,34 +550,40 @@ int frames_core(Decoder *d, const uint8_t *host_syms, int nframes, int framebits
     CU(cudaMemcpyAsync(d->dsyms, host_syms, fsyms * (size_t)nframes, cudaMemcpyHostToDevice, st));
     const int L = std::max(8, d->chain_seg & ~7);
     const uint32_t nseg = ((uint32_t)framebits + L - 1) / L;
-    for (int i = 0; i < S; i++) {
-        if (grow((void **)&D[i]->seg, &D[i]->seg_cap, 2 * (size_t)nseg * sizeof(uint32_t))) return -1;
-        CU(cudaStreamSynchronize(D[i]->stream));
-    }
-    for (int f0 = 0; f0 < nframes; f0 += S) {
+    for (int k = 0; k < nsets; k++)
+        for (int i = 0; i < S; i++) {
+            if (grow((void **)&D[k][i]->seg, &D[k][i]->seg_cap, 2 * (size_t)nseg * sizeof(uint32_t))) return -1;
+            CU(cudaStreamSynchronize(D[k][i]->stream));
+        }
+    CU(cudaStreamSynchronize(st));                       // the symbols are on the device before any other stream reads them
+    int group = 0;
+    for (int f0 = 0; f0 < nframes; f0 += S, group++) {
+        Decoder **G = D[nsets == 2 ? (group & 1) : 0];
+        cudaStream_t sg = G[0]->stream;                  // the set's ACS stream (its first decoder's)
         const int nb = std::min(S, nframes - f0);
         const uint8_t *sp[MAX_CTX];
+        // the set's previous tracebacks (two groups back) are through before its rings and metrics are written again;
+        // they ran while the other set was in its ACS passes
+        for (int i = 1; i < S; i++) CU(cudaStreamSynchronize(G[i]->stream));
         for (int i = 0; i < nb; i++) {
-            D[i]->cache_valid = 0;
+            G[i]->cache_valid = 0;
             const uint32_t ss = (start_states ? start_states[f0 + i] : 0u) & STATEMASK;
-            CU(launch_init(D[i]->metrics[0], D[i]->ctl, ss, INIT_BIAS, 0, st));                 // init_viterbi224(start), viterbi224_sse2.c:37-53
-            CU(cudaMemcpyAsync(D[i]->h_ctl, D[i]->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, st));
+            CU(launch_init(G[i]->metrics[0], G[i]->ctl, ss, INIT_BIAS, 0, sg));                 // init_viterbi224(start), viterbi224_sse2.c:37-53
+            CU(cudaMemcpyAsync(G[i]->h_ctl, G[i]->ctl, CTL_HOST_BYTES, cudaMemcpyDeviceToHost, sg));
             sp[i] = d->dsyms + fsyms * (size_t)(f0 + i);
         }
-        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamSynchronize(sg));
         d->launches += nb;
-        if (multi_update_core(D, sp, nb, framebits, nullptr)) return -1;
-        // The group's tracebacks are independent chains of dependent ring loads (latency, not bandwidth): each runs on its
-        // own decoder's stream so that they overlap instead of queueing behind one another (the update above has completed:
-        // multi_update_core ends with a synchronisation).  All are through before the next group re-uses the rings.
+        if (multi_update_core(G, sp, nb, framebits, nullptr)) return -1;         // ends with a synchronisation: the rows are written
         for (int i = 0; i < nb; i++) {
             const uint32_t es = end_states ? end_states[f0 + i] : 0u;
-            CU(launch_chainback(trace_args(D[i]), (uint32_t)framebits, es, L, d->chain_warm, d->dout + fbytes * (size_t)(f0 + i), D[i]->seg, D[i]->seg + nseg,
-                                D[i]->d_redo, D[i]->stream));
+            CU(launch_chainback(trace_args(G[i]), (uint32_t)framebits, es, L, d->chain_warm, d->dout + fbytes * (size_t)(f0 + i), G[i]->seg, G[i]->seg + nseg,
+                                G[i]->d_redo, G[i]->stream));
             d->launches += 2;
         }
-        for (int i = 1; i < nb; i++) CU(cudaStreamSynchronize(D[i]->stream));
     }
+    for (int k = 0; k < nsets; k++)
+        for (int i = 0; i < S; i++) CU(cudaStreamSynchronize(D[k][i]->stream));
     CU(cudaMemcpyAsync(host_data, d->dout, fbytes * (size_t)nframes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return 0;
@@ -770,7 +787,7 @@ void delete_viterbi224(void *p)
     Decoder *d = as_dec(p);
     if (!d) return;
     // the next create_viterbi224 of the same size gets this decoder back (decode.c:216-229 deletes and creates per frame)
-    for (int i = 0; i < MAX_CTX - 1; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
+    for (int i = 0; i < NAUX; i++) if (d->aux[i]) { destroy(d->aux[i]); d->aux[i] = nullptr; }
     Decoder *evict = nullptr;
     bool pooled = false;
     if (d->ring_bytes <= POOL_MAX_BYTES / 2 && cudaSetDevice(d->dev) == cudaSuccess && cudaStreamSynchronize(d->stream) == cudaSuccess) {
