@@ -33,6 +33,8 @@
 #include <vector>
 #include <chrono>
 #include <unistd.h>
+#include <poll.h>
+#include <cerrno>
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
 #include "hostfmt.h"
@@ -61,22 +63,31 @@ void sync_taps(int taps[SYNCBITS])
 }
 
 // stdin as a window over the symbol stream, addressed by absolute symbol index: have(n) blocks until symbols [.., n)
-// are there (false at end of input), drop_before(a) forgets what lies in front of a.
+// are there (false at end of input), have_now(n) only takes what is already waiting in the pipe (a live symdemod delivers
+// about a thousand symbols per second: a speculative batch must not sit and wait for frames that have not been received
+// yet), drop_before(a) forgets what lies in front of a.  read(2) returns what is there; fread would hold out for full buffers.
 struct Input {
     std::vector<unsigned char> buf;
     unsigned long long origin = 0;      // absolute index of buf[0]
     bool eof = false;
-    bool have(unsigned long long n)
+    bool fill(unsigned long long n, bool wait)
     {
         while (origin + buf.size() < n && !eof) {
+            if (!wait) {
+                struct pollfd pf = {0, POLLIN, 0};
+                if (poll(&pf, 1, 0) <= 0) break;                 // nothing waiting right now
+            }
             const size_t old = buf.size(), need = (size_t)(n - origin) - old, want = need > (1u << 16) ? need : (1u << 16);
             buf.resize(old + want);
-            const size_t got = fread(buf.data() + old, 1, want, stdin);
-            buf.resize(old + got);
-            if (got == 0) eof = true;
+            const ssize_t got = read(0, buf.data() + old, want);
+            buf.resize(old + (got > 0 ? (size_t)got : 0));
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) eof = true;
         }
         return origin + buf.size() >= n;
     }
+    bool have(unsigned long long n) { return fill(n, true); }
+    bool have_now(unsigned long long n) { return fill(n, false); }
     const unsigned char *at(unsigned long long a) const { return buf.data() + (size_t)(a - origin); }
     void drop_before(unsigned long long a)
     {
@@ -203,7 +214,7 @@ int main(int argc, char *argv[])
         // a run of frames, 2048 symbols apart: as many as are complete, at most `batch`
         const unsigned long long first = base + sync_start + SYNCBITS;
         int nb = 1;
-        while (nb < batch && in.have(first + (unsigned long long)(nb + 1) * FRAMESYMBOLS)) nb++;
+        while (nb < batch && in.have_now(first + (unsigned long long)(nb + 1) * FRAMESYMBOLS)) nb++;
 
         // 1. Fano on the host for every frame of the run (decode.c:196-204; the cycle limit it passes is the constant 100)
         if (fano_enabled) {

@@ -25,6 +25,7 @@
 #include <clocale>
 #include <vector>
 #include <unistd.h>
+#include <cerrno>
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
 #include "hostfmt.h"
@@ -41,6 +42,17 @@ constexpr int RING = 4096;                // vdecode's symbol history (vdecode.c
 constexpr unsigned long long SYNCWORD = 0x12fc819fbeull;   // decode.c:24; the correlator taps are its encoding
 
 inline int parity64(unsigned long long x) { return __builtin_parityll(x); }
+
+// read(2) hands over what has arrived (fread would hold out for a full buffer -- minutes on a live 1 ksymbol/s stream,
+// on top of the one block of latency -B asks for); 0 at end of input
+inline ssize_t read_some(unsigned char *dst, size_t cap)
+{
+    for (;;) {
+        const ssize_t got = read(0, dst, cap);
+        if (got < 0 && errno == EINTR) continue;
+        return got;
+    }
+}
 
 // The 34 encoded sync symbols (vdecode.c:27-30 lists them as constants; they are the tail of encode(SYNCWORD)).
 void sync_taps(int taps[NTAPS])
@@ -198,16 +210,16 @@ int main(int argc, char *argv[])
 
     if (framing && bits_in) {
         for (;;) {
-            const size_t got = fread(inbuf.data(), 1, inbuf.size(), stdin);
-            if (got == 0) break;
-            for (size_t p = 0; p < got; p++) frame_bit(inbuf[p] == '1');      // framer.c:65: anything but '1' counts as 0
+            const ssize_t got = read_some(inbuf.data(), inbuf.size());
+            if (got <= 0) break;
+            for (ssize_t p = 0; p < got; p++) frame_bit(inbuf[p] == '1');      // framer.c:65: anything but '1' counts as 0
         }
         return 0;
     }
     for (;;) {
-        const size_t got = fread(inbuf.data(), 1, inbuf.size(), stdin);
-        if (got == 0) break;
-        for (size_t p = 0; p < got; p++) {
+        const ssize_t got = read_some(inbuf.data(), inbuf.size());
+        if (got <= 0) break;
+        for (ssize_t p = 0; p < got; p++) {
             const unsigned char c = inbuf[p];
             hist[slot] = c;
             if ((slot & 1) == 0) even_sym = c;

@@ -317,3 +317,45 @@ def test_host_programs_on_empty_short_and_ragged_input(built):
         if os.path.exists(ref):
             want = subprocess.run([ref], input=txt, capture_output=True, timeout=60, env=env)
             assert got.stdout == want.stdout, bits[:50]
+
+
+def _feed_slowly(cmd, data, chunks, env=None):
+    """Run cmd with `data` trickling into its stdin in pieces (a live pipe: reads return short counts, polls find nothing waiting)."""
+    import time
+    p = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    import threading
+    out = {}
+    t = threading.Thread(target=lambda: out.update(stdout=p.stdout.read(), stderr=p.stderr.read()))
+    t.start()
+    pos = 0
+    for n in chunks:
+        if pos >= len(data):
+            break
+        p.stdin.write(data[pos: pos + n]); p.stdin.flush()
+        pos += n
+        time.sleep(0.001)
+    p.stdin.write(data[pos:])
+    p.stdin.close()
+    t.join(120)
+    assert p.wait(60) == 0, out.get("stderr")
+    return out["stdout"]
+
+
+def test_host_programs_give_the_same_output_on_a_trickling_pipe(built):
+    """The block drivers read with read(2) and extend a speculative frame batch only with frames that have already
+    arrived; what they print must not depend on how the input is chopped up in time."""
+    vb = os.path.join(ROOT, "isee3-decoder_b200", "bin", "vdecode_block")
+    db = os.path.join(ROOT, "isee3-decoder_b200", "bin", "decode_block")
+    env = dict(os.environ, LANG="C")
+    rng = np.random.default_rng(12)
+    _, soft = S.telemetry_stream(30 * 1024, 2.0, seed=41, junk_symbols=321)
+    data = soft.tobytes()
+    chunks = [int(x) for x in rng.integers(1, 5000, 400)]
+    for cmd in ([db, "-F"], [db, "-F", "-n", "-B", "4"], [db, "-S"], [vb, "-P", "-q"], [vb, "-P", "-q", "-B", "1500"]):
+        whole = subprocess.run(cmd, input=data, capture_output=True, timeout=120, env=env)
+        assert whole.returncode == 0
+        assert _feed_slowly(cmd, data, chunks, env) == whole.stdout, cmd
+    bits = np.unpackbits(_host_golden("framer_seed7")["bits"])
+    txt = bytes(np.where(bits == 1, ord("1"), ord("0")).astype(np.uint8))
+    whole = subprocess.run([vb, "-f", "-b"], input=txt, capture_output=True, timeout=60, env=env)
+    assert _feed_slowly([vb, "-f", "-b"], txt, [int(x) for x in rng.integers(1, 300, 100)], env) == whole.stdout
