@@ -84,6 +84,73 @@ int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int fra
  * favoured (start_state < 0), or init_viterbi224 semantics (start_state >= 0). */
 int v224x_init_uniform(void *p, int bias, int start_state);
 
+/* ---- host side of the streaming driver (vdecode.c:101-140,186) ---------------------------------------------
+ * Which received symbols form the pairs vdecode hands to update_viterbi224_blk: the 34-tap sync correlator over the
+ * last 4096 symbols, the once-per-frame comparison of the in-phase and out-of-phase peaks, and the one-symbol slip of
+ * a phase flip (the symbol at the decision is dropped, the next one is paired with the stale even-slot symbol).
+ * Host arithmetic only (north_star keeps the phase flip on the host); no GPU needed.
+ *   soft / nsyms : received soft symbols (symdemod byte format, symdemod.c:240-251)
+ *   start_phase  : vdecode -p (vdecode.c:77);   dontflip : vdecode -F (vdecode.c:71)
+ *   pairs_out    : 2 bytes per pair, room for nsyms / 2 + 1 pairs
+ *   cmp_out      : NULL, or 2 bytes per pair: the hard-sliced symbols vdecode compares the re-encoded pair with
+ *                  (vdecode.c:176-177, for decode delay `delay`)
+ *   flip_at      : NULL, or room for flip_cap entries: index of the first pair after each phase flip; *nflips = how many
+ * Returns the number of pairs, -1 on bad arguments. */
+long long v224x_pair_symbols(const unsigned char *soft, long long nsyms, int start_phase, int dontflip, int delay,
+                             unsigned char *pairs_out, unsigned char *cmp_out, long long *flip_at, int flip_cap, int *nflips);
+
+/* ---- time segments of one stream on several GPUs (vdecode.c:145-152 per range) --------------------
+ * A stream of pairs is cut into contiguous output ranges, one per GPU.  The decoder of a range that does not begin the
+ * stream starts `lead` = delay + conv stages early from uniform metrics; it makes the decisions of the sequential
+ * decoder from the stage at which the two path-metric vectors differ by a constant.  That is CHECKED: the later range
+ * saves its metrics `delay` stages before its first output (every row its tracebacks touch lies after that point), the
+ * earlier range saves its metrics at the same stream position, and the two snapshots must differ by a constant
+ * (v224x_metric_spread_dev == 0).  If they do not, the earlier range's decoder -- exact at its end -- decodes the later
+ * range again (lead = 0).  The stitched output is therefore always what one sequential decoder produces.
+ *
+ * v224x_range_decode: one range on this handle's GPU.  syms = the pairs of stream stages [first - lead, first + nout).
+ *   lead == 0 : the handle continues from its current state (stream start after init_viterbi224, or the previous call)
+ *   lead  > 0 : the handle restarts from uniform metrics, the first `lead` stages give no output
+ *   bits_out[i] = what decodebit(delay, 0) returns after stage lead + i            (nout entries)
+ *   snap_early_dev : NULL or 16 MiB of device memory: metrics after stage lead - delay        (needs lead >= delay)
+ *   snap_late_dev  : NULL or 16 MiB of device memory: metrics after stage lead + nout - delay (needs nout >= delay)
+ *   nseg, conv, report : as for v224x_stream_decode_seg (the range itself runs as nseg lockstep segments on its GPU)
+ * The _dev variant takes syms / bits_out in device memory of the handle's GPU.  Returns 0, -1 on error. */
+int v224x_range_decode(void *p, const unsigned char *syms, int lead, int nout, int delay, unsigned char *bits_out, int nseg, int conv,
+                       void *snap_early_dev, void *snap_late_dev, v224x_seg_report *report);
+int v224x_range_decode_dev(void *p, const unsigned char *dev_syms, int lead, int nout, int delay, unsigned char *dev_bits_out, int nseg,
+                           int conv, void *snap_early_dev, void *snap_late_dev, v224x_seg_report *report);
+/* max - min over all 2^23 states of (a[s] - b[s]) for two metric snapshots in device memory of the handle's GPU:
+ * 0 <=> the vectors differ by a constant <=> the two decoders make identical decisions from there on. */
+int v224x_metric_spread_dev(void *p, const void *dev_a, const void *dev_b, int *spread_out);
+size_t v224x_snapshot_bytes(void);
+
+/* The same inside one process: one host thread and one CUDA stream per GPU, snapshots moved with peer copies.
+ * devices[ngpu] = CUDA device ordinals (NULL: 0 .. ngpu-1); ring_rows = decision-ring rows per decoder (> delay; the
+ * stream is worked through in chunks of ring_rows - delay stages).  The context owns one decoder per GPU (plus the
+ * lockstep partners of nseg > 1) and keeps the stream's state between calls: v224x_multi_init = init_viterbi224 for the
+ * stream, every v224x_multi_stream_decode call continues where the last one ended (block-wise callers such as
+ * vdecode_block -G N); the range that begins a block runs on the GPU that holds that state. */
+typedef struct v224x_multi v224x_multi;
+typedef struct {
+    int gpus;                 /* ranges (= GPUs) used for this call (short inputs use fewer)                        */
+    int handovers_verified;   /* GPU-to-GPU hand-overs whose snapshot check passed                                 */
+    int ranges_redone;        /* ranges decoded again by the previous range's decoder because a check failed       */
+    int worst_spread;         /* largest snapshot spread seen at a GPU-to-GPU check (0 = every range had converged) */
+    int inner_verified;       /* sums of the per-GPU reports (lockstep segments inside each range)                 */
+    int inner_redone;
+    long long extra_stages;   /* trellis stages run on top of nbits (warm-ups and redone ranges / segments)        */
+    long long residual_diffs; /* output bits that can differ from the sequential decode: 0 by construction         */
+} v224x_multi_report;
+v224x_multi *v224x_multi_create(const int *devices, int ngpu, int ring_rows);
+int  v224x_multi_init(v224x_multi *m, int starting_state);
+int  v224x_multi_stream_decode(v224x_multi *m, const unsigned char *syms, long long nbits, int delay, unsigned char *bits_out,
+                               int nseg, int conv, v224x_multi_report *report);
+void v224x_multi_delete(v224x_multi *m);
+
+/* Give pooled device memory (recycled decoders and rings of deleted handles) back to the driver. */
+void v224x_trim(void);
+
 /* ---- device memory helpers for callers without a CUDA runtime of their own ------------ */
 void *v224x_dev_alloc(void *p, size_t bytes);
 void  v224x_dev_free(void *p, void *dev_ptr);

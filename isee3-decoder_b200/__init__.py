@@ -11,7 +11,7 @@ reference's streaming driver vdecode.c.
 There is no CPU decoding path: loading fails loudly if the CUDA library is missing, and
 ``Viterbi224(...)`` raises if no CUDA device is usable.
 """
-from .binding import (Viterbi224, V224Error, load_library, library_path, device_count, NSTATES, ROWWORDS,  # noqa: F401
+from .binding import (Viterbi224, MultiGpu, pair_symbols, V224Error, load_library, library_path, device_count, NSTATES, ROWWORDS,  # noqa: F401
                       ABI_SYMBOLS, EXT_SYMBOLS)
 from . import streams  # noqa: F401
 from . import vdecode  # noqa: F401

@@ -17,7 +17,9 @@ EXT_SYMBOLS = ["v224x_device_count", "v224x_set_device", "v224x_last_error", "v2
                "v224x_stream_decode_dev", "v224x_stream_decode_seg", "v224x_stream_decode_seg_dev", "v224x_decode_frames", "v224x_update_dev", "v224x_update_multi_dev", "v224x_init_uniform", "v224x_dev_alloc", "v224x_dev_free",
                "v224x_h2d", "v224x_d2h", "v224x_host_alloc_pinned", "v224x_host_free_pinned", "v224x_timer_start",
                "v224x_timer_stop_ms", "v224x_kernel_time_reset", "v224x_kernel_time_enable", "v224x_kernel_time_ms", "v224x_kernel_time_passes",
-               "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option"]
+               "v224x_get_stats", "v224x_get_metrics", "v224x_set_state", "v224x_get_row", "v224x_set_option",
+               "v224x_pair_symbols", "v224x_range_decode", "v224x_range_decode_dev", "v224x_metric_spread_dev", "v224x_snapshot_bytes",
+               "v224x_multi_create", "v224x_multi_init", "v224x_multi_stream_decode", "v224x_multi_delete", "v224x_trim"]
 
 
 class V224Error(RuntimeError):
@@ -29,6 +31,12 @@ class Stats(ctypes.Structure):
                 ("single_stages", ctypes.c_ulonglong), ("sat_stages", ctypes.c_ulonglong), ("invalidated_passes", ctypes.c_ulonglong),
                 ("chainback_redo", ctypes.c_ulonglong),
                 ("renormals", ctypes.c_longlong), ("stages", ctypes.c_longlong), ("walk_steps", ctypes.c_ulonglong)]
+
+
+class MultiReport(ctypes.Structure):
+    _fields_ = [("gpus", ctypes.c_int), ("handovers_verified", ctypes.c_int), ("ranges_redone", ctypes.c_int), ("worst_spread", ctypes.c_int),
+                ("inner_verified", ctypes.c_int), ("inner_redone", ctypes.c_int), ("extra_stages", ctypes.c_longlong),
+                ("residual_diffs", ctypes.c_longlong)]
 
 
 class SegReport(ctypes.Structure):
@@ -92,6 +100,16 @@ def load_library():
         "v224x_set_state": (ci, [vp, vp, cll, cll]),
         "v224x_get_row": (ci, [vp, ci, vp]),
         "v224x_set_option": (ci, [vp, ctypes.c_char_p, cll]),
+        "v224x_pair_symbols": (cll, [vp, cll, ci, ci, ci, vp, vp, vp, ci, ctypes.POINTER(ci)]),
+        "v224x_range_decode": (ci, [vp, vp, ci, ci, ci, vp, ci, ci, vp, vp, vp]),
+        "v224x_range_decode_dev": (ci, [vp, vp, ci, ci, ci, vp, ci, ci, vp, vp, vp]),
+        "v224x_metric_spread_dev": (ci, [vp, vp, vp, ctypes.POINTER(ci)]),
+        "v224x_snapshot_bytes": (ctypes.c_size_t, []),
+        "v224x_multi_create": (vp, [vp, ci, ci]),
+        "v224x_multi_init": (ci, [vp, ci]),
+        "v224x_multi_stream_decode": (ci, [vp, vp, cll, ci, vp, ci, ci, vp]),
+        "v224x_multi_delete": (None, [vp]),
+        "v224x_trim": (None, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -103,6 +121,72 @@ def load_library():
 
 def device_count():
     return load_library().v224x_device_count()
+
+
+def pair_symbols(soft, start_phase=0, dontflip=False, delay=200, want_cmp=False):
+    """v224x_pair_symbols: the pairs vdecode.c:101-140 hands to the decoder for the received symbols `soft` (host
+    arithmetic, no GPU).  Returns (pairs uint8[n, 2], flips list) or (pairs, flips, cmp uint8[n, 2]) with want_cmp."""
+    lib = load_library()
+    a = np.ascontiguousarray(soft, dtype=np.uint8)
+    cap = a.size // 2 + 1
+    out = np.empty(2 * cap, dtype=np.uint8)
+    cmp_ = np.empty(2 * cap, dtype=np.uint8) if want_cmp else None
+    flips = np.zeros(4096, dtype=np.int64)
+    nf = ctypes.c_int(0)
+    n = lib.v224x_pair_symbols(a.ctypes.data_as(ctypes.c_void_p), a.size, int(start_phase), int(bool(dontflip)), int(delay),
+                               out.ctypes.data_as(ctypes.c_void_p), None if cmp_ is None else cmp_.ctypes.data_as(ctypes.c_void_p),
+                               flips.ctypes.data_as(ctypes.c_void_p), flips.size, ctypes.byref(nf))
+    if n < 0:
+        raise V224Error("v224x_pair_symbols failed")
+    pairs = out[:2 * n].reshape(-1, 2)
+    fl = [int(x) for x in flips[:min(nf.value, flips.size)]]
+    return (pairs, fl, cmp_[:2 * n].reshape(-1, 2)) if want_cmp else (pairs, fl)
+
+
+class MultiGpu:
+    """v224x_multi_*: one stream decoded as time segments on several GPUs of this process (one host thread and one
+    stream per GPU inside the library, hand-overs verified with peer copies of the metric snapshots)."""
+
+    def __init__(self, ngpu, ring_rows, devices=None):
+        self.lib = load_library()
+        devs = None
+        if devices is not None:
+            devs = (ctypes.c_int * ngpu)(*devices)
+        self.h = self.lib.v224x_multi_create(devs, int(ngpu), int(ring_rows))
+        if not self.h:
+            raise V224Error("v224x_multi_create failed: " + (self.lib.v224x_last_error() or b"").decode())
+
+    def init(self, starting_state=0):
+        if self.lib.v224x_multi_init(self.h, int(starting_state)) < 0:
+            raise V224Error("v224x_multi_init failed: " + (self.lib.v224x_last_error() or b"").decode())
+
+    def stream_decode(self, syms, delay, nseg=3, conv=-1, nbits=None, out=None):
+        a, p = _u8(syms)
+        n = a.size // 2 if nbits is None else int(nbits)
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        rep = MultiReport()
+        rc = self.lib.v224x_multi_stream_decode(self.h, p, n, int(delay), out.ctypes.data_as(ctypes.c_void_p), int(nseg), int(conv), ctypes.byref(rep))
+        if rc < 0:
+            raise V224Error("v224x_multi_stream_decode failed: " + (self.lib.v224x_last_error() or b"").decode())
+        return out, {k: getattr(rep, k) for k, _ in MultiReport._fields_}
+
+    def delete(self):
+        if getattr(self, "h", None):
+            self.lib.v224x_multi_delete(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.delete()
+
+    def __del__(self):
+        try:
+            self.delete()
+        except Exception:
+            pass
 
 
 def _u8(a):
@@ -205,6 +289,29 @@ class Viterbi224:
         self._check(self.lib.v224x_stream_decode_seg_dev(self.h, dev_syms, int(nbits), int(delay), dev_bits, int(nseg), int(conv),
                                                          ctypes.byref(rep)), "v224x_stream_decode_seg_dev")
         return {k: getattr(rep, k) for k, _ in SegReport._fields_}
+
+    def range_decode(self, syms, lead, nout, delay, nseg=3, conv=-1, snap_early=None, snap_late=None):
+        """v224x_range_decode: one time segment of a longer stream (host buffers).  snap_early / snap_late: device
+        pointers (16 MiB each) or None.  Returns (bits uint8[nout], report dict)."""
+        a, p = _u8(syms)
+        assert a.size >= 2 * (lead + nout)
+        out = np.empty(nout, dtype=np.uint8)
+        rep = SegReport()
+        self._check(self.lib.v224x_range_decode(self.h, p, int(lead), int(nout), int(delay), out.ctypes.data_as(ctypes.c_void_p), int(nseg),
+                                                int(conv), snap_early, snap_late, ctypes.byref(rep)), "v224x_range_decode")
+        return out, {k: getattr(rep, k) for k, _ in SegReport._fields_}
+
+    def range_decode_dev(self, dev_syms, lead, nout, delay, dev_bits, nseg=3, conv=-1, snap_early=None, snap_late=None):
+        rep = SegReport()
+        self._check(self.lib.v224x_range_decode_dev(self.h, dev_syms, int(lead), int(nout), int(delay), dev_bits, int(nseg), int(conv),
+                                                    snap_early, snap_late, ctypes.byref(rep)), "v224x_range_decode_dev")
+        return {k: getattr(rep, k) for k, _ in SegReport._fields_}
+
+    def metric_spread_dev(self, dev_a, dev_b):
+        """0 <=> the two metric snapshots differ by a constant (the two decoders are in step)."""
+        out = ctypes.c_int(0)
+        self._check(self.lib.v224x_metric_spread_dev(self.h, dev_a, dev_b, ctypes.byref(out)), "v224x_metric_spread_dev")
+        return int(out.value)
 
     def decode_frames(self, syms, nframes, framebits, start_states=None, end_states=None, nlock=3):
         """v224x_decode_frames: nframes independent frames (init / update / chainback each), nlock side by side.

@@ -10,7 +10,8 @@ LIB = os.path.join(HERE, "libviterbi224_b200.so")
 # (source, extra nvcc flags).  The fused ACS pass is compiled with ptxas -O1: at the default level ptxas reorders the
 # decision-bit gather behind a whole stage of butterflies and spills; in source order the tile body needs no spill.
 SOURCES = [("v224_acs_persist.cu", ["-Xptxas", "-O1"]), ("v224_kernels.cu", []), ("v224_runtime.cu", [])]
-HEADERS = ["v224_common.cuh", "v224_fused_core.cuh", "v224_kernels.h",
+HOST_SOURCES = ["v224_pairing.cpp"]           # plain C++ (g++ -O3): host-side entries of the library, no CUDA
+HEADERS = ["v224_common.cuh", "v224_fused_core.cuh", "v224_kernels.h", "v224_pairing.cpp", os.path.join("..", "host", "pairing.h"),
            os.path.join("..", "..", "include", "viterbi224.h"), os.path.join("..", "..", "include", "viterbi224_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--cudart", "static", "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
@@ -33,7 +34,7 @@ def is_stale():
 
 HOST_PROGRAMS = {"vdecode_block": os.path.join(HERE, "host", "vdecode_block.cpp"),
                  "decode_block": os.path.join(HERE, "host", "decode_block.cpp")}
-HOST_HEADERS = [os.path.join(HERE, "host", "hostfmt.h"), os.path.join(HERE, "host", "fano_seq.h")]
+HOST_HEADERS = [os.path.join(HERE, "host", "hostfmt.h"), os.path.join(HERE, "host", "fano_seq.h"), os.path.join(HERE, "host", "pairing.h")]
 BIN = os.path.join(HERE, "bin")
 
 
@@ -44,7 +45,7 @@ def build_host_programs(force=False):
     for name, src in HOST_PROGRAMS.items():
         exe = os.path.join(BIN, name)
         if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(LIB), *map(os.path.getmtime, HOST_HEADERS)):
-            cmd = ["g++", "-O2", "-Wall", "-std=c++17", "-o", exe, src, "-L" + HERE, "-lviterbi224_b200", "-Wl,-rpath,$ORIGIN/.."]
+            cmd = ["g++", "-O3", "-Wall", "-std=c++17", "-o", exe, src, "-L" + HERE, "-lviterbi224_b200", "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("host program build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -68,6 +69,13 @@ def build_library(force=False, verbose=False, out=None, extra_flags=()):
         log.append(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        objs.append(o)
+    for s in HOST_SOURCES:
+        o = (out + "." if variant else os.path.join(CSRC, "")) + s.replace(".cpp", ".o")
+        cmd = ["g++", "-O3", "-std=c++17", "-Wall", "-fPIC", "-c", "-o", o, os.path.join(CSRC, s)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         objs.append(o)
     lib = out if variant else LIB
     cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs]

@@ -18,6 +18,7 @@
 #include "v224_common.cuh"
 #include "v224_fused_core.cuh"
 #include "v224_kernels.h"
+#include <mutex>
 #include <cuda.h>          // CUtensorMap and the cuTensorMapEncodeTiled prototype only; the entry point is fetched at run time
 
 namespace v224 {
@@ -358,10 +359,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
 // ------------------------------------------------------------------------------------------
 constexpr unsigned SPIN_LIMIT = 20u * 1000u * 1000u;      // polls of >= 20-40 ns: seconds.  A wait that long means a broken invariant.
 
-__device__ __forceinline__ void slot_reset(PassSlot &s)
+__device__ __forceinline__ void slot_reset(PassSlot &s, int pass)
 {
     stats_reset(s.st);
-    s.done_word = 0;
+    s.done_word = done_word_fresh(pass);          // no tile done yet, tagged with the pass the slot now serves
 }
 
 __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T)
@@ -373,7 +374,7 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long lon
     pc.force_careful = force_careful;
     pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
     pc.maxR_prev = c->maxR;
-    for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i]); pc.slot[i].pass_word = 0; }
+    for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i], i); pc.slot[i].pass_word = 0; }
     const int careful0 = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     const int careful1 = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
     pc.slot[0].pass_word = make_pass_word(0, careful0, c->sub);
@@ -440,7 +441,7 @@ __device__ void resolve_persist(Ctl *c, int n)
         if (careful) c->n_careful++;
         // parameters of pass n+2 (its slot is free: pass n-2 is long resolved)
         PassSlot &nx = pc.slot[(n + 2) % PSLOTS];
-        slot_reset(nx);
+        slot_reset(nx, n + 2);
         const int sub1 = (int)(*(volatile unsigned long long *)&pc.slot[(n + 1) % PSLOTS].pass_word & 0x7fffffffu);
         const int careful2 = pc.force_careful || ((long long)z + O + 510ll * 2 * FK >= RENORM_TRIGGER);
         if (!careful2 && (long long)mx + O + 510ll * 2 * FK > 32767) {
@@ -508,7 +509,10 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
             const unsigned long long dwd = __shfl_sync(0xffffffffu, v, 2);
             stopped = n >= stop;
             // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
-            const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) && (n == 0 || done_class_count(dwd, tau >> 8) >= 256u);
+            // (the slots are recycled every PSLOTS passes: the done word carries the pass it counts for, so a stale word of
+            // pass n - 1 - PSLOTS can never read as "complete")
+            const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) &&
+                               (n == 0 || (done_word_pass(dwd) == (unsigned)((n - 1) & 0xffff) && done_class_count(dwd, tau >> 8) >= 256u));
             if (stopped || ready) break;
             if (spins > SPIN_LIMIT) {            // a wait that lasts seconds means a broken invariant: flag it, never hang the GPU
                 if (lane == 0) { atomicOr((unsigned *)&a.ctl->error, 16u); atomicMin(&pc.stop_pass, 0); }
@@ -571,7 +575,7 @@ __device__ void retirer_warp(FusedSmem &sm, const MultiArgs &m)
             // before the tile counts as done
             const unsigned long long old = atom_acq_rel_add64(&sl.done_word, done_increment(tau % TILE_CLASSES));
             TRACE(TKEY(n, s), tau, 6);
-            if ((unsigned)(old & 0xffffffffu) == FUSED_TILES - 1) resolve_persist(c, n);
+            if (done_total(old) == FUSED_TILES - 1) resolve_persist(c, n);
             TRACE(TKEY(n, s), tau, 7);
         }
         __syncwarp();
@@ -631,6 +635,8 @@ cudaError_t build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cu
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
+    static std::mutex encode_mu;
+    std::lock_guard<std::mutex> encode_lk(encode_mu);
     if (!encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -659,26 +665,36 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
 {
     int dev = 0;
     cudaGetDevice(&dev);
-    static int checked[64], slots[64];
-    if (dev >= 0 && dev < 64 && !checked[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-        if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, CTA_THREADS, sizeof(FusedSmem));
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        slots[dev] = per_sm * sms;
-        checked[dev] = 1;
+    // per-device launch geometry, looked up once; callers may come from several host threads (one per GPU)
+    constexpr int MAXDEV = 64;
+    static std::mutex mu;
+    static int checked[MAXDEV], slots[MAXDEV];
+    if (dev < 0 || dev >= MAXDEV) return cudaErrorInvalidDevice;
+    int nslots = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!checked[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(k_acs_persist, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int per_sm = 0, sms = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_acs_persist, CTA_THREADS, sizeof(FusedSmem));
+            if (e != cudaSuccess) return e;
+            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            slots[dev] = per_sm * sms;
+            checked[dev] = 1;
+        }
+        nslots = slots[dev];
     }
+    if (m.grid_limit > 0 && m.grid_limit < nslots) nslots = m.grid_limit;
     for (int s = 0; s < m.nctx; s++) {
         const PersistArgs &a = m.ctx[s];
         k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
         k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0);
     }
     const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
-    const int grid = (int)(items < slots[dev] ? items : slots[dev]);
+    const int grid = (int)(items < nslots ? items : nslots);
     k_acs_persist<<<grid, CTA_THREADS, sizeof(FusedSmem), st>>>(m);
     return cudaGetLastError();
 }

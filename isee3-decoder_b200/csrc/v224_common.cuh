@@ -116,7 +116,8 @@ __host__ __device__ inline unsigned stats_max(const PassStats &s)
 
 // Bookkeeping of one in-flight pass of the persistent kernel.  Two 64-bit words carry everything a tile's protocol
 // warp has to poll, so that one round of parallel loads decides "may this tile start":
-//   done_word = [63:48] class-1 tiles done | [47:32] class-0 tiles done | [31:0] tiles done   (class = tile index mod 2)
+//   done_word = [63:48] class-1 tiles done | [47:32] class-0 tiles done | [31:16] pass number mod 2^16 | [15:0] tiles done
+//               (class = tile index mod 2; the pass tag is written when the slot is reset for that pass)
 //   pass_word = (pass number + 1) << 32 | careful << 31 | sub     published by the resolver of pass n-2 (or the launch)
 struct PassSlot {
     PassStats st;
@@ -129,6 +130,9 @@ __host__ __device__ inline unsigned long long make_pass_word(int n, int careful,
 }
 __host__ __device__ inline unsigned done_class_count(unsigned long long w, unsigned cls) { return (unsigned)(w >> (32 + 16 * cls)) & 0xffffu; }
 __host__ __device__ inline unsigned long long done_increment(unsigned cls) { return 1ull | (1ull << (32 + 16 * cls)); }
+__host__ __device__ inline unsigned long long done_word_fresh(int pass) { return (unsigned long long)((unsigned)pass & 0xffffu) << 16; }
+__host__ __device__ inline unsigned done_word_pass(unsigned long long w) { return (unsigned)(w >> 16) & 0xffffu; }
+__host__ __device__ inline unsigned done_total(unsigned long long w) { return (unsigned)w & 0xffffu; }
 static_assert(TILE_CLASSES == 2, "done_word layout");
 struct PersistCtl {
     unsigned next_item;     // dynamic work queue head: item = pass * 512 + order index

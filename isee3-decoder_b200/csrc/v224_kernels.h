@@ -26,6 +26,7 @@ constexpr int MAX_CTX = 4;
 struct MultiArgs {
     int nctx;
     int npasses;             // per context
+    int grid_limit;          // 0: one CTA per resident slot (148 SMs x CTAs per SM); > 0: at most this many CTAs
     PersistArgs ctx[MAX_CTX];
 };
 

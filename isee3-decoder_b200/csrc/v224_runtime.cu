@@ -10,6 +10,8 @@
 #include <cstdarg>
 #include <mutex>
 #include <vector>
+#include <string>
+#include <thread>
 #include <algorithm>
 #include "v224_kernels.h"
 #include "../../include/viterbi224.h"
@@ -48,6 +50,8 @@ std::vector<PoolEntry> g_pool;
 constexpr size_t POOL_MAX_ENTRIES = 4;
 constexpr size_t POOL_MAX_BYTES = (size_t)24 << 30;      // cached rings never hold more than this (oldest are released first)
 
+void release_parked_decoders();      // defined below the Decoder type
+
 void *pool_get(int dev, size_t bytes)
 {
     {
@@ -61,13 +65,16 @@ void *pool_get(int dev, size_t bytes)
     }
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
-        // release cached rings and retry once
+        // release everything that is only parked -- recycled decoders (each holds a ring) and cached rings -- and retry once
+        cudaGetLastError();
+        release_parked_decoders();
         std::vector<PoolEntry> drop;
         {
             std::lock_guard<std::mutex> lk(g_pool_mu);
             drop.swap(g_pool);
         }
-        for (auto &e : drop) cudaFree(e.ptr);
+        for (auto &e : drop) { cudaSetDevice(e.dev); cudaFree(e.ptr); }
+        cudaSetDevice(dev);
         cudaGetLastError();
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
@@ -75,7 +82,7 @@ void *pool_get(int dev, size_t bytes)
 }
 void pool_put(int dev, size_t bytes, void *ptr)
 {
-    std::vector<void *> evict;
+    std::vector<PoolEntry> evict;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         g_pool.push_back({dev, bytes, ptr});
@@ -83,11 +90,12 @@ void pool_put(int dev, size_t bytes, void *ptr)
         for (auto &e : g_pool) total += e.bytes;
         while (!g_pool.empty() && (g_pool.size() > POOL_MAX_ENTRIES || total > POOL_MAX_BYTES)) {
             total -= g_pool.front().bytes;
-            evict.push_back(g_pool.front().ptr);
+            evict.push_back(g_pool.front());
             g_pool.erase(g_pool.begin());
         }
     }
-    for (void *q : evict) cudaFree(q);
+    for (auto &e : evict) { cudaSetDevice(e.dev); cudaFree(e.ptr); }
+    if (!evict.empty()) cudaSetDevice(dev);
 }
 
 struct Decoder {
@@ -123,10 +131,11 @@ struct Decoder {
     int *d_segdiff;            // [2 * MAX_CTX]: min / max of the metric difference at each hand-over check
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache;
+    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache, grid_limit;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     long long stages_total;                // trellis stages ever run on this ring (how many rows a recycled decoder has to clear)
+    int ring_dirty_all;                    // v224x_set_state moved the stage counter: rows were not written from row 0 upwards
     double acs_ms;
     int time_kernels;
 };
@@ -197,6 +206,16 @@ void destroy(Decoder *d)
     free(d);
 }
 
+void release_parked_decoders()
+{
+    std::vector<Decoder *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_dec_mu);
+        drop.swap(g_dec_pool);
+    }
+    for (Decoder *d : drop) { d->magic = MAGIC; destroy(d); }
+}
+
 int do_init(Decoder *d, int bias, int start_state)
 {
     if (bind(d)) return -1;
@@ -216,13 +235,15 @@ int recycle(Decoder *d)
 {
     if (bind(d)) return -1;
     d->magic = MAGIC;
-    d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = 0;
+    d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = d->grid_limit = 0;
     d->chain_seg = 128;
     d->chain_warm = 256;
     d->launches = d->acs_launches_timed = d->acs_passes_timed = d->chainback_redo = 0;
     d->acs_ms = 0;
     d->time_kernels = 0;
-    const size_t rows = (size_t)std::min<long long>(d->len, std::max<long long>(0, d->stages_total));
+    // rows are written from row 0 upwards unless v224x_set_state moved the stage counter: then any row may be dirty
+    const size_t rows = d->ring_dirty_all ? (size_t)d->len : (size_t)std::min<long long>(d->len, std::max<long long>(0, d->stages_total));
+    d->ring_dirty_all = 0;
     if (rows) {
         CU(cudaMemsetAsync(d->ring, 0, rows * ROWBYTES, d->stream));
         CU(cudaMemsetAsync(d->row_fmt, 0, rows, d->stream));
@@ -256,13 +277,16 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         if (fuse && end - p >= FK) {
             // one persistent launch runs all full passes of this batch as a dataflow ("per_pass_launch": one launch per pass)
             const int total = (end - p) / FK;
-            const int per_launch = d->per_pass_launch ? 1 : total;
+            // two passes of one persistent launch may be in flight at once: with fewer than 2 * FK ring rows they would
+            // write the same row, so such rings get one launch per pass
+            const int per_launch = (d->per_pass_launch || d->len < 2 * FK) ? 1 : total;
             if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(per_launch))) return -1;
             for (int done_p = 0; done_p < total; done_p += per_launch) {
                 const int npasses = std::min(per_launch, total - done_p);
                 MultiArgs m;
                 m.nctx = 1;
                 m.npasses = npasses;
+                m.grid_limit = d->grid_limit;
                 m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->tmaps, d->optab, d->len, p,
                                        (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
                 CU(launch_persist(m, d->stream));
@@ -321,13 +345,14 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
     int pos = 0;
     bool lockstep = true;
     for (int s = 0; s < nctx; s++) ds[s]->stages_total += nbits;
-    for (int s = 0; s < nctx; s++) if (ds[s]->force_single || ds[s]->force_sat) lockstep = false;
+    for (int s = 0; s < nctx; s++) if (ds[s]->force_single || ds[s]->force_sat || ds[s]->len < 2 * FK) lockstep = false;
     while (lockstep && pos < fused_total) {
         const int end = std::min(fused_total, pos + BATCH_STAGES);
         const int npasses = (end - pos) / FK;
         MultiArgs m;
         m.nctx = nctx;
         m.npasses = npasses;
+        m.grid_limit = d0->grid_limit;
         for (int s = 0; s < nctx; s++) {
             Decoder *d = ds[s];
             if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
@@ -372,30 +397,55 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
     return 0;
 }
 
-int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
+// A metric snapshot request of a range decode: after local stage `at` of the range (stages [0, at) applied) the exact
+// decoder's current metric buffer is copied to `dst` (16 MiB of device memory on this GPU).  dst == nullptr: none.
+struct Snap { int at; uint16_t *dst; };
+
+int take_snaps(Decoder *d, int pos, const Snap *snaps, int nsnaps, cudaStream_t st)
+{
+    for (int k = 0; k < nsnaps; k++)
+        if (snaps[k].dst && snaps[k].at == pos)
+            CU(cudaMemcpyAsync(snaps[k].dst, d->metrics[d->h_ctl->cur], METRICBYTES, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// Stream decode of nbits stages starting at local stage `base` of a range whose first `lead` stages are warm-up
+// (no output): the output of local stage t >= lead goes to dev_bits[t - lead].  Snapshot positions are range-local.
+int stream_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits, int base = 0, int lead = 0,
+                const Snap *snaps = nullptr, int nsnaps = 0)
 {
     if (delay <= 0 || delay >= d->len) { set_err("stream decode needs 0 < delay < len (delay %d, len %d)", delay, d->len); return -1; }
     const int chunk_max = d->len - delay;
     int renorms = 0;
+    if (take_snaps(d, base, snaps, nsnaps, d->stream)) return -1;
     for (int done = 0; done < nbits;) {
-        const int n = std::min(chunk_max, nbits - done);
+        int n = std::min(chunk_max, nbits - done);
+        for (int k = 0; k < nsnaps; k++) {
+            const int rel = snaps[k].at - base - done;
+            if (snaps[k].dst && rel > 0 && rel < n) n = rel;
+        }
         const long long T_first = d->h_ctl->T;
         const int r = update_core(d, dev_syms + 2 * (size_t)done, n);
         if (r < 0) return -1;
         renorms += r;
-        CU(launch_stream_trace(trace_args(d), T_first, n, delay, dev_bits + done, d->stream));
-        d->launches++;
+        const int o0 = std::max(0, lead - base - done);           // first stage of this chunk that emits
+        if (o0 < n) {
+            CU(launch_stream_trace(trace_args(d), T_first + o0, n - o0, delay, dev_bits + (base + done + o0 - lead), d->stream));
+            d->launches++;
+        }
         done += n;
+        if (take_snaps(d, base + done, snaps, nsnaps, d->stream)) return -1;
     }
     CU(cudaStreamSynchronize(d->stream));
     return renorms;
 }
 
 // stream_core on another decoder of the same call: its own stream, after everything queued on `st` so far.
-int stream_core_on(Decoder *h, cudaStream_t st, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits)
+int stream_core_on(Decoder *h, cudaStream_t st, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits, int base, int lead,
+                   const Snap *snaps, int nsnaps)
 {
     CU(cudaStreamSynchronize(st));
-    return stream_core(h, dev_syms, nbits, delay, dev_bits);
+    return stream_core(h, dev_syms, nbits, delay, dev_bits, base, lead, snaps, nsnaps);
 }
 
 // Exchange everything but identity (the handle address the caller holds, the list of auxiliary decoders, options).
@@ -412,6 +462,7 @@ void swap_bodies(Decoder *d, Decoder *o)
     o->ev0 = to.ev0; o->ev1 = to.ev1; o->kev0 = to.kev0; o->kev1 = to.kev1;
     d->force_single = td.force_single; d->force_sat = td.force_sat; d->force_careful = td.force_careful;
     d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm; d->no_walk_cache = td.no_walk_cache;
+    d->grid_limit = td.grid_limit;
     d->time_kernels = td.time_kernels; d->acs_ms = td.acs_ms; d->acs_launches_timed = td.acs_launches_timed;
     d->acs_passes_timed = td.acs_passes_timed; d->launches = td.launches;
     o->time_kernels = to.time_kernels; o->acs_ms = to.acs_ms; o->acs_launches_timed = to.acs_launches_timed;
@@ -438,7 +489,11 @@ Decoder *make_aux(Decoder *d)
     return a;
 }
 
-int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits, int nseg, int conv, v224x_seg_report *rep)
+// `lead` leading stages are warm-up of the whole range (multi-GPU time segments: the caller started the handle from uniform
+// metrics); the output of local stage t >= lead goes to dev_bits[t - lead].  nbits = all local stages (lead included).
+// Snapshots (range-local positions) are taken from the decoder that is exact at that position.
+int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t *dev_bits, int nseg, int conv, v224x_seg_report *rep,
+             int lead = 0, const Snap *snaps = nullptr, int nsnaps = 0)
 {
     if (delay <= 0 || delay >= d->len) { set_err("stream decode needs 0 < delay < len (delay %d, len %d)", delay, d->len); return -1; }
     if (conv < 0) conv = 2048;
@@ -446,8 +501,17 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
     int S = std::max(1, std::min(nseg, MAX_CTX));
     constexpr int MIN_SEG = 4096;                        // not worth a warm-up below this
     while (S > 1 && (long long)nbits < (long long)S * (W + MIN_SEG)) S--;
+    // the first decoder carries the range's own warm-up and its early snapshot; the last one the late snapshot
+    while (S > 1) {
+        const int A_ = ((nbits - W) / S) & ~7;
+        bool ok = A_ >= delay && lead < A_ + W;
+        for (int k = 0; k < nsnaps; k++)
+            if (snaps[k].dst && !(snaps[k].at <= A_ + W || snaps[k].at >= (S - 1) * A_ + W)) ok = false;   // a decoder's own warm-up is not exact
+        if (ok) break;
+        S--;
+    }
     if (rep) { rep->segments = S; rep->warm = S > 1 ? W : 0; rep->verified = 0; rep->redone = 0; rep->extra_stages = 0; rep->worst_spread = 0; }
-    if (S == 1) return stream_core(d, dev_syms, nbits, delay, dev_bits);
+    if (S == 1) return stream_core(d, dev_syms, nbits, delay, dev_bits, 0, lead, snaps, nsnaps);
 
     const int A = ((nbits - W) / S) & ~7;                 // lockstep length of a segment's own range
     const int Ltot = A + W;                               // local stages every decoder runs in lockstep
@@ -463,25 +527,36 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
     }
     if (!d->d_segdiff) CU(cudaMalloc(&d->d_segdiff, 2 * MAX_CTX * sizeof(int)));
     for (int i = 0; i < S; i++) {
-        sy[i] = dev_syms + 2 * (size_t)i * A;             // decoder i runs stream stages [i*A, i*A + Ltot)
+        sy[i] = dev_syms + 2 * (size_t)i * A;             // decoder i runs range stages [i*A, i*A + Ltot)
         T0[i] = D[i]->h_ctl->T;
         CU(cudaStreamSynchronize(D[i]->stream));
     }
     cudaStream_t st = d->stream;
     const int chunk_max = d->len - delay;
     const int check_early = conv, check_late = Ltot - delay;       // local stage of the two sides of a hand-over check
+    // range snapshots inside the lockstep part: positions of decoder 0 (early) and of decoder S-1 (late), in loop-local stages
+    int stops[2 + 2 * 4];
+    int nstops = 0;
+    stops[nstops++] = check_early;
+    stops[nstops++] = check_late;
+    for (int k = 0; k < nsnaps && k < 4; k++) {
+        if (!snaps[k].dst) continue;
+        if (snaps[k].at <= Ltot) stops[nstops++] = snaps[k].at;                                   // decoder 0 is exact there
+        else if (snaps[k].at <= (S - 1) * A + Ltot) stops[nstops++] = snaps[k].at - (S - 1) * A;  // the last decoder's own range
+    }
+    if (take_snaps(D[0], 0, snaps, nsnaps, st)) return -1;
     int a = 0;
     while (a < Ltot) {
         int b = std::min(Ltot, a + chunk_max);
-        if (a < check_early && b > check_early) b = check_early;
-        if (a < check_late && b > check_late) b = check_late;
+        for (int k = 0; k < nstops; k++) if (a < stops[k] && b > stops[k]) b = stops[k];
         const uint8_t *sp[MAX_CTX];
         for (int i = 0; i < S; i++) sp[i] = sy[i] + 2 * (size_t)a;
         if (multi_update_core(D, sp, S, b - a, nullptr)) return -1;
         for (int i = 0; i < S; i++) {
-            const int o0 = std::max(a, i ? W : 0);        // decoder i >= 1 emits nothing inside its warm-up
+            // decoder i >= 1 emits nothing inside its warm-up, nobody inside the range's
+            const int o0 = std::max(std::max(a, i ? W : 0), lead - i * A);
             if (o0 < b) {
-                CU(launch_stream_trace(trace_args(D[i]), T0[i] + o0, b - o0, delay, dev_bits + (size_t)i * A + o0, st));
+                CU(launch_stream_trace(trace_args(D[i]), T0[i] + o0, b - o0, delay, dev_bits + ((size_t)i * A + o0 - lead), st));
                 d->launches++;
             }
         }
@@ -492,6 +567,12 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
                 CU(launch_metric_diff(D[i]->metrics[D[i]->h_ctl->cur], D[i + 1]->snap, d->d_segdiff + 2 * i, st));
                 d->launches++;
             }
+        // range snapshots: the first decoder is exact by definition, the last one if every hand-over check passes
+        // (otherwise the sequential redo below passes the position again and overwrites the snapshot)
+        if (take_snaps(D[0], b, snaps, nsnaps, st)) return -1;
+        for (int k = 0; k < nsnaps; k++)
+            if (snaps[k].dst && snaps[k].at > Ltot && snaps[k].at - (S - 1) * A == b)
+                CU(cudaMemcpyAsync(snaps[k].dst, D[S - 1]->metrics[D[S - 1]->h_ctl->cur], METRICBYTES, cudaMemcpyDeviceToDevice, st));
         a = b;
     }
     int diff[2 * MAX_CTX];
@@ -501,15 +582,15 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
     for (int i = 0; i + 1 < S; i++) {
         const int spread = diff[2 * i + 1] - diff[2 * i];
         if (rep && spread > rep->worst_spread) rep->worst_spread = spread;
-        if (spread != 0) { head = i; break; }             // decoder i+1 had not converged: everything after decoder i is redone
+        if (spread != 0) { head = i; break; }               // decoder i+1 had not converged: everything after decoder i is redone
         if (rep) rep->verified++;
     }
     // the tail: what is left after the lockstep part, or -- after a failed check -- everything from decoder `head`'s end
-    const int done_upto = (head + 1) * A + W;              // stream stages decoded exactly so far
+    const int done_upto = (head + 1) * A + W;              // range stages decoded exactly so far
     if (rep) { rep->redone = S - 1 - head; rep->extra_stages = (long long)(S - 1) * W + (long long)(S - 1 - head) * A; }
     if (done_upto < nbits) {
         Decoder *h = D[head];
-        if (stream_core_on(h, st, dev_syms + 2 * (size_t)done_upto, nbits - done_upto, delay, dev_bits + done_upto) < 0) return -1;
+        if (stream_core_on(h, st, dev_syms + 2 * (size_t)done_upto, nbits - done_upto, delay, dev_bits, done_upto, lead, snaps, nsnaps) < 0) return -1;
     }
     CU(cudaStreamSynchronize(st));
     if (head != 0) swap_bodies(d, D[head]);               // the caller's handle continues the stream from its end
@@ -586,6 +667,172 @@ int frames_core(Decoder *d, const uint8_t *host_syms, int nframes, int framebits
         for (int i = 0; i < S; i++) CU(cudaStreamSynchronize(D[k][i]->stream));
     CU(cudaMemcpyAsync(host_data, d->dout, fbytes * (size_t)nframes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+
+// ---- one time segment of a longer stream (multi-GPU decode) -----------------------------------
+// Range-local stages [0, lead + nout); the first `lead` are warm-up from uniform metrics (lead == 0: the handle's
+// current state continues).  Snapshots: early after stage lead - delay, late after stage lead + nout - delay.
+int range_core(Decoder *d, const uint8_t *dev_syms, int lead, int nout, int delay, uint8_t *dev_bits, int nseg, int conv,
+               uint16_t *snap_early, uint16_t *snap_late, v224x_seg_report *rep)
+{
+    if (lead < 0 || nout < 0) { set_err("range decode: negative length"); return -1; }
+    if (snap_early && lead < delay) { set_err("range decode: the early snapshot needs lead >= delay (lead %d, delay %d)", lead, delay); return -1; }
+    if (snap_late && nout < delay) { set_err("range decode: the late snapshot needs nout >= delay (nout %d, delay %d)", nout, delay); return -1; }
+    if (lead > 0 && do_init(d, INIT_BIAS, -1)) return -1;        // mid-stream start: no state is favoured
+    Snap snaps[2] = {{lead - delay, snap_early}, {lead + nout - delay, snap_late}};
+    if (lead + nout == 0) return 0;
+    return seg_core(d, dev_syms, lead + nout, delay, dev_bits, nseg, conv, rep, lead, snaps, 2) < 0 ? -1 : 0;
+}
+
+int spread_core(Decoder *d, const uint16_t *a, const uint16_t *b, int *spread_out)
+{
+    if (!d->d_segdiff) CU(cudaMalloc(&d->d_segdiff, 2 * MAX_CTX * sizeof(int)));
+    CU(launch_metric_diff(a, b, d->d_segdiff, d->stream));
+    d->launches++;
+    int diff[2];
+    CU(cudaMemcpyAsync(diff, d->d_segdiff, sizeof diff, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    *spread_out = diff[1] - diff[0];
+    return 0;
+}
+
+} // namespace
+
+// ---- the multi-GPU context ------------------------------------------------------------------
+constexpr int MULTI_MAX = 16;
+struct v224x_multi {
+    int n;
+    int devs[MULTI_MAX];
+    Decoder *dec[MULTI_MAX];
+    uint16_t *snap_early[MULTI_MAX], *snap_late[MULTI_MAX], *snap_peer[MULTI_MAX];   // on the slot's own GPU
+    uint8_t *dsyms[MULTI_MAX], *dbits[MULTI_MAX];
+    size_t dsyms_cap[MULTI_MAX], dbits_cap[MULTI_MAX];
+    int head;                      // slot whose decoder holds the state at the end of the stream decoded so far
+    int ring_rows;
+};
+
+namespace {
+
+struct RangeJob {
+    int slot;
+    long long first;               // first output stage of the range (stream position inside this call)
+    int lead, nout;
+    bool want_early, want_late;
+    v224x_seg_report rep;
+    int rc;
+    std::string err;
+};
+
+// Decode one range on its slot's GPU: symbols in, bits out (host memory of the caller), snapshots left on the GPU.
+void run_range(v224x_multi *m, RangeJob *j, const unsigned char *syms, int delay, unsigned char *bits_out, int nseg, int conv)
+{
+    j->rc = -1;
+    const int k = j->slot;
+    Decoder *d = m->dec[k];
+    do {
+        if (bind(d)) break;
+        const size_t nsym = 2 * ((size_t)j->lead + (size_t)j->nout);
+        if (grow((void **)&m->dsyms[k], &m->dsyms_cap[k], nsym)) break;
+        if (grow((void **)&m->dbits[k], &m->dbits_cap[k], (size_t)j->nout)) break;
+        if (cudaMemcpyAsync(m->dsyms[k], syms + 2 * (size_t)(j->first - j->lead), nsym, cudaMemcpyHostToDevice, d->stream) != cudaSuccess) {
+            set_err("range %lld: copying the symbols to device %d failed: %s", j->first, d->dev, cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (range_core(d, m->dsyms[k], j->lead, j->nout, delay, m->dbits[k], nseg, conv, j->want_early ? m->snap_early[k] : nullptr,
+                       j->want_late ? m->snap_late[k] : nullptr, &j->rep))
+            break;
+        if (cudaMemcpyAsync(bits_out + j->first, m->dbits[k], (size_t)j->nout, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+            cudaStreamSynchronize(d->stream) != cudaSuccess) {
+            set_err("range %lld: copying the decoded bits back from device %d failed: %s", j->first, d->dev, cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        j->rc = 0;
+    } while (0);
+    if (j->rc) j->err = g_err;                  // g_err is per thread: hand the text to the caller's thread
+}
+
+// Is the decoder of slot `later` (early snapshot) in step with the decoder of slot `earlier` (late snapshot)?
+int handover_spread(v224x_multi *m, int earlier, int later, int *spread)
+{
+    Decoder *d = m->dec[earlier];
+    if (bind(d)) return -1;
+    const uint16_t *other = m->snap_early[later];
+    if (m->devs[earlier] != m->devs[later]) {
+        // 16 MiB over NVLink (peer copy; the runtime stages it through the host where peer access is not possible)
+        CU(cudaMemcpyPeerAsync(m->snap_peer[earlier], m->devs[earlier], m->snap_early[later], m->devs[later], METRICBYTES, d->stream));
+        other = m->snap_peer[earlier];
+    }
+    return spread_core(d, m->snap_late[earlier], other, spread);
+}
+
+int multi_core(v224x_multi *m, const unsigned char *syms, long long nbits, int delay, unsigned char *bits_out, int nseg, int conv,
+               v224x_multi_report *rep)
+{
+    if (delay <= 0 || delay >= m->ring_rows) { set_err("multi decode needs 0 < delay < ring rows (delay %d, rows %d)", delay, m->ring_rows); return -1; }
+    if (nbits > 0x7fffffffll - 65536) { set_err("multi decode: at most 2^31 - 65536 bits per call"); return -1; }
+    if (conv < 0) conv = 2048;
+    const int W = delay + conv;
+    // a range pays its warm-up; below a few warm-ups of output it is not worth a GPU
+    int G = m->n;
+    const long long min_range = std::max<long long>(4ll * W, 16384);
+    while (G > 1 && nbits / G < min_range) G--;
+    if (rep) { memset(rep, 0, sizeof *rep); rep->gpus = G; }
+    RangeJob jobs[MULTI_MAX];
+    for (int g = 0; g < G; g++) {
+        RangeJob &j = jobs[g];
+        j.slot = (m->head + g) % m->n;
+        j.first = nbits * g / G;
+        const long long last = nbits * (g + 1) / G;
+        j.lead = g ? W : 0;
+        j.nout = (int)(last - j.first);
+        j.want_early = g > 0;
+        j.want_late = g + 1 < G;
+        j.rc = 0;
+        memset(&j.rep, 0, sizeof j.rep);
+    }
+    {
+        // one host thread per GPU for the duration of the call (the calling thread takes the first range)
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; g++) th.emplace_back(run_range, m, &jobs[g], syms, delay, bits_out, nseg, conv);
+        run_range(m, &jobs[0], syms, delay, bits_out, nseg, conv);
+        for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < G; g++)
+        if (jobs[g].rc) { set_err("multi decode, range %d on device %d: %s", g, m->devs[jobs[g].slot], jobs[g].err.c_str()); return -1; }
+    // hand-overs, in stream order; a range whose decoder had not converged is decoded again by the decoder that is
+    // exact at the range's start (the one that produced the previous range's accepted output)
+    int exact = jobs[0].slot;
+    for (int g = 1; g < G; g++) {
+        int spread = 0;
+        if (handover_spread(m, exact, jobs[g].slot, &spread)) return -1;
+        if (rep && spread > rep->worst_spread) rep->worst_spread = spread;
+        if (spread == 0) {
+            if (rep) rep->handovers_verified++;
+            exact = jobs[g].slot;
+            continue;
+        }
+        RangeJob redo = jobs[g];
+        redo.slot = exact;
+        redo.lead = 0;
+        redo.want_early = false;
+        run_range(m, &redo, syms, delay, bits_out, nseg, conv);
+        if (redo.rc) { set_err("multi decode, range %d again on device %d: %s", g, m->devs[exact], redo.err.c_str()); return -1; }
+        if (rep) {
+            rep->ranges_redone++;
+            rep->extra_stages += redo.nout + redo.rep.extra_stages;
+            rep->inner_verified += redo.rep.verified;
+            rep->inner_redone += redo.rep.redone;
+        }
+    }
+    m->head = exact;
+    if (rep)
+        for (int g = 0; g < G; g++) {
+            rep->extra_stages += jobs[g].lead + jobs[g].rep.extra_stages;
+            rep->inner_verified += jobs[g].rep.verified;
+            rep->inner_redone += jobs[g].rep.redone;
+        }
     return 0;
 }
 
@@ -907,6 +1154,124 @@ int v224x_stream_decode_seg(void *p, const unsigned char *syms, int nbits, int d
     return 0;
 }
 
+int v224x_range_decode_dev(void *p, const unsigned char *dev_syms, int lead, int nout, int delay, unsigned char *dev_bits_out, int nseg,
+                           int conv, void *snap_early_dev, void *snap_late_dev, v224x_seg_report *rep)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (bind(d)) return -1;
+    return range_core(d, dev_syms, lead, nout, delay, dev_bits_out, nseg, conv, static_cast<uint16_t *>(snap_early_dev),
+                      static_cast<uint16_t *>(snap_late_dev), rep);
+}
+
+int v224x_range_decode(void *p, const unsigned char *syms, int lead, int nout, int delay, unsigned char *bits_out, int nseg, int conv,
+                       void *snap_early_dev, void *snap_late_dev, v224x_seg_report *rep)
+{
+    Decoder *d = as_dec(p);
+    if (!d) return -1;
+    if (lead < 0 || nout < 0) { set_err("range decode: negative length"); return -1; }
+    if (bind(d)) return -1;
+    const size_t n = (size_t)lead + (size_t)nout;
+    if (grow((void **)&d->dsyms, &d->dsyms_cap, 2 * n)) return -1;
+    if (grow((void **)&d->dout, &d->dout_cap, (size_t)nout)) return -1;
+    CU(cudaMemcpyAsync(d->dsyms, syms, 2 * n, cudaMemcpyHostToDevice, d->stream));
+    uint8_t *dsyms = d->dsyms, *dout = d->dout;          // the handle's body may be exchanged with the last segment's decoder
+    if (range_core(d, dsyms, lead, nout, delay, dout, nseg, conv, static_cast<uint16_t *>(snap_early_dev), static_cast<uint16_t *>(snap_late_dev), rep))
+        return -1;
+    CU(cudaMemcpyAsync(bits_out, dout, (size_t)nout, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+int v224x_metric_spread_dev(void *p, const void *dev_a, const void *dev_b, int *spread_out)
+{
+    Decoder *d = as_dec(p);
+    if (!d || !dev_a || !dev_b || !spread_out) return -1;
+    if (bind(d)) return -1;
+    return spread_core(d, static_cast<const uint16_t *>(dev_a), static_cast<const uint16_t *>(dev_b), spread_out);
+}
+
+size_t v224x_snapshot_bytes(void) { return METRICBYTES; }
+
+void v224x_multi_delete(v224x_multi *m)
+{
+    if (!m) return;
+    for (int k = 0; k < m->n; k++) {
+        if (cudaSetDevice(m->devs[k]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (m->dec[k]) { m->dec[k]->magic = MAGIC; destroy(m->dec[k]); }
+        cudaFree(m->snap_early[k]); cudaFree(m->snap_late[k]); cudaFree(m->snap_peer[k]);
+        cudaFree(m->dsyms[k]); cudaFree(m->dbits[k]);
+    }
+    cudaGetLastError();
+    free(m);
+}
+
+v224x_multi *v224x_multi_create(const int *devices, int ngpu, int ring_rows)
+{
+    const int ndev = v224x_device_count();
+    if (ngpu < 1 || ngpu > MULTI_MAX || ngpu > ndev) { set_err("v224x_multi_create: %d GPUs asked for, %d visible (1..%d supported)", ngpu, ndev, MULTI_MAX); return nullptr; }
+    v224x_multi *m = static_cast<v224x_multi *>(calloc(1, sizeof(v224x_multi)));
+    if (!m) return nullptr;
+    m->n = ngpu;
+    m->ring_rows = ring_rows;
+    const int saved = g_device;
+    for (int k = 0; k < ngpu; k++) {
+        m->devs[k] = devices ? devices[k] : k;
+        bool ok = m->devs[k] >= 0 && m->devs[k] < ndev;
+        for (int t = 0; t < k; t++) ok = ok && m->devs[t] != m->devs[k];
+        if (!ok) { set_err("v224x_multi_create: bad or repeated device %d", m->devs[k]); g_device = saved; v224x_multi_delete(m); return nullptr; }
+        g_device = m->devs[k];
+        m->dec[k] = static_cast<Decoder *>(create_viterbi224(ring_rows));
+        ok = m->dec[k] != nullptr;
+        ok = ok && cudaMalloc(&m->snap_early[k], METRICBYTES) == cudaSuccess && cudaMalloc(&m->snap_late[k], METRICBYTES) == cudaSuccess &&
+             cudaMalloc(&m->snap_peer[k], METRICBYTES) == cudaSuccess;
+        if (!ok) {
+            if (m->dec[k]) set_err("v224x_multi_create: snapshot buffers on device %d: %s", m->devs[k], cudaGetErrorString(cudaGetLastError()));
+            g_device = saved;
+            v224x_multi_delete(m);
+            return nullptr;
+        }
+    }
+    g_device = saved;
+    // peer access makes the snapshot copies direct NVLink transfers (without it the runtime stages them through the host)
+    for (int a = 0; a < ngpu; a++)
+        for (int b = 0; b < ngpu; b++) {
+            int can = 0;
+            if (a == b || cudaDeviceCanAccessPeer(&can, m->devs[a], m->devs[b]) != cudaSuccess || !can) continue;
+            if (cudaSetDevice(m->devs[a]) == cudaSuccess) cudaDeviceEnablePeerAccess(m->devs[b], 0);
+            cudaGetLastError();                  // "already enabled" is fine
+        }
+    m->head = 0;
+    return m;
+}
+
+int v224x_multi_init(v224x_multi *m, int starting_state)
+{
+    if (!m) return -1;
+    m->head = 0;
+    return do_init(m->dec[0], INIT_BIAS, (int)((uint32_t)starting_state & STATEMASK));      // init_viterbi224 for the stream
+}
+
+int v224x_multi_stream_decode(v224x_multi *m, const unsigned char *syms, long long nbits, int delay, unsigned char *bits_out, int nseg,
+                              int conv, v224x_multi_report *rep)
+{
+    if (!m || !syms || !bits_out) { set_err("v224x_multi_stream_decode: NULL argument"); return -1; }
+    if (nbits <= 0) { if (rep) memset(rep, 0, sizeof *rep); return 0; }
+    return multi_core(m, syms, nbits, delay, bits_out, nseg <= 0 ? 3 : nseg, conv, rep);
+}
+
+void v224x_trim(void)
+{
+    release_parked_decoders();
+    std::vector<PoolEntry> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        drop.swap(g_pool);
+    }
+    for (auto &e : drop) { cudaSetDevice(e.dev); cudaFree(e.ptr); }
+    cudaGetLastError();
+}
+
 int v224x_decode_frames(void *p, const unsigned char *syms, int nframes, int framebits, const unsigned int *start_states,
                         const unsigned int *end_states, unsigned char *data_out, int nlock)
 {
@@ -1049,6 +1414,7 @@ int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, l
     Decoder *d = as_dec(p);
     if (!d || bind(d)) return -1;
     d->cache_valid = 0;
+    d->ring_dirty_all = 1;
     int16_t *tmp = nullptr;
     CU(cudaMalloc(&tmp, METRICBYTES));
     int rc = 0;
@@ -1089,6 +1455,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "force_careful")) d->force_careful = (int)value;
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
     else if (!strcmp(key, "no_walk_cache")) d->no_walk_cache = (int)value;
+    else if (!strcmp(key, "grid_limit")) d->grid_limit = (int)std::max(0ll, value);
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

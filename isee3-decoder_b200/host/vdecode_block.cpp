@@ -12,7 +12,10 @@
 // what the per-bit loop returns).  Everything vdecode derives from decoder output (start-up suppression, the
 // re-encode symbol-error tally, the status lines) is replayed per pair afterwards from values recorded on the way in.
 //
-// Extra options: -B pairs  block size (default 262144; latency = one block), -S n  decoders in lockstep (default 4),
+// Extra options: -B pairs  block size (default 262144 per GPU; latency = one block), -S n  decoders in lockstep per GPU (default 4),
+// -G n  GPUs: every block is cut into n time segments decoded side by side, one per GPU (v224x_multi_stream_decode: every
+// GPU-to-GPU hand-over verified on the device, a range whose decoder had not converged is decoded again -- the output
+// is the one-GPU output), -v  a summary of the hand-over checks on stderr at the end,
 // -P  pairs only: write the symbol pairs that would go to the decoder (2 bytes each) to stdout and exit -- no GPU needed;
 // the CPU test tier checks the pairing / phase-flip logic through it.
 // -f  frames instead of bits: standard output is what `vdecode | framer` prints (framer.c:61-95: a 1024-bit shift
@@ -29,17 +32,14 @@
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
 #include "hostfmt.h"
+#include "pairing.h"
 
 namespace {
 
-// code constants of the reference's active code block (code.h:54-63)
-constexpr int K = 24;
-constexpr unsigned long long POLY1 = 073665667ull, POLY2 = 073665665ull;
-constexpr int G1FLIP = 0, G2FLIP = 1;
-constexpr int FRAME_SYMBOLS = 2048;       // symbols per minor frame (vdecode.c:14-15)
-constexpr int NTAPS = 34;                 // usable encoded sync symbols (vdecode.c:16)
-constexpr int RING = 4096;                // vdecode's symbol history (vdecode.c:20); its size shows in the tally, so it is kept
-constexpr unsigned long long SYNCWORD = 0x12fc819fbeull;   // decode.c:24; the correlator taps are its encoding
+using v224host::SymbolPairer;
+constexpr int K = SymbolPairer::K;
+constexpr unsigned long long POLY1 = SymbolPairer::POLY1, POLY2 = SymbolPairer::POLY2, SYNCWORD = SymbolPairer::SYNCWORD;
+constexpr int G1FLIP = SymbolPairer::G1FLIP, G2FLIP = SymbolPairer::G2FLIP;
 
 inline int parity64(unsigned long long x) { return __builtin_parityll(x); }
 
@@ -54,34 +54,17 @@ inline ssize_t read_some(unsigned char *dst, size_t cap)
     }
 }
 
-// The 34 encoded sync symbols (vdecode.c:27-30 lists them as constants; they are the tail of encode(SYNCWORD)).
-void sync_taps(int taps[NTAPS])
-{
-    int sym[80];
-    unsigned long long reg = 0;
-    for (int i = 39; i >= 0; i--) {
-        reg = (reg << 1) | ((SYNCWORD >> i) & 1);
-        sym[2 * (39 - i)] = G1FLIP ^ parity64(reg & POLY1);
-        sym[2 * (39 - i) + 1] = G2FLIP ^ parity64(reg & POLY2);
-    }
-    for (int k = 0; k < NTAPS; k++) taps[k] = sym[80 - NTAPS + k];
-}
-
-struct PairRec {
-    unsigned char s0, s1;     // the pair handed to the decoder
-    unsigned char c1, c2;     // hard-sliced history symbols vdecode compares the re-encoded pair with (vdecode.c:176-177)
-};
-
 } // namespace
 
 int main(int argc, char *argv[])
 {
     int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4, pairs_only = 0, framing = 0, bitrate = 512, bits_in = 0;
-    long block = 262144;
+    int ngpu = 1, verbose = 0;
+    long block = 0;
     const char *lang = getenv("LANG");
     setlocale(LC_ALL, lang ? lang : "en_US.utf8");                       // vdecode.c:59-62 (thousands separators in the status line)
     int opt;
-    while ((opt = getopt(argc, argv, "d:pi:qFB:S:Pfr:b")) != -1) {
+    while ((opt = getopt(argc, argv, "d:pi:qFB:S:Pfr:bG:v")) != -1) {
         switch (opt) {
         case 'F': dontflip = 1; break;
         case 'q': quiet = 1; break;
@@ -94,6 +77,8 @@ int main(int argc, char *argv[])
         case 'f': framing = 1; break;
         case 'b': bits_in = 1; break;
         case 'r': bitrate = atoi(optarg); break;
+        case 'G': ngpu = atoi(optarg); break;
+        case 'v': verbose = 1; break;
         default: break;
         }
     }
@@ -103,30 +88,35 @@ int main(int argc, char *argv[])
     } else if (delay > 1024) {
         fprintf(stderr, "%s: Warning; excessive decode delay; 1MB/bit needed\n", argv[0]);
     }
+    if (ngpu < 1) ngpu = 1;
+    if (block <= 0) block = 262144l * ngpu;
     if (block < 1024) block = 1024;
     const int ring_rows = delay + 8192;                                   // the library works through a block in chunks of (rows - delay)
     void *vd = nullptr;
+    v224x_multi *vm = nullptr;
     if (!pairs_only && !(framing && bits_in)) {
-        vd = create_viterbi224(ring_rows);
-        if (!vd) { fprintf(stderr, "%s: create_viterbi224 failed: %s\n", argv[0], v224x_last_error()); return 1; }
-        init_viterbi224(vd, 0);                                           // vdecode.c:96
+        if (ngpu > 1) {
+            vm = v224x_multi_create(nullptr, ngpu, ring_rows);
+            if (!vm) { fprintf(stderr, "%s: v224x_multi_create failed: %s\n", argv[0], v224x_last_error()); return 1; }
+            v224x_multi_init(vm, 0);
+        } else {
+            vd = create_viterbi224(ring_rows);
+            if (!vd) { fprintf(stderr, "%s: create_viterbi224 failed: %s\n", argv[0], v224x_last_error()); return 1; }
+            init_viterbi224(vd, 0);                                       // vdecode.c:96
+        }
     }
 
-    int taps[NTAPS];
-    sync_taps(taps);
-    unsigned char hist[RING];
-    for (int i = 0; i < RING; i += 2) { hist[i] = G1FLIP ? 255 : 0; hist[i + 1] = G2FLIP ? 255 : 0; }    // vdecode.c:55-58
-    int slot = phase;                    // ring slot of the next input symbol; its low bit is the decoder's symbol phase
-    unsigned char even_sym = 0;          // the last symbol that landed on an even slot (first half of the next pair)
-    int frame_count = 0, peak_in = -1000000, peak_out = -1000000;
-    const int back = 2 * (delay + K - 2);
-
-    std::vector<PairRec> pairs;
+    // vdecode's pairing and phase-flip logic (vdecode.c:101-140), run ahead of the decoder
+    SymbolPairer pairer(phase, dontflip != 0, delay);
+    std::vector<unsigned long long> flips_abs;      // index (since the start of the stream) of the first pair after each phase flip
+    unsigned long long pairs_before = 0;            // pairs of earlier blocks
     std::vector<size_t> flip_at;         // a phase flip happened before the pair with this index (for the notice's place on stderr)
-    std::vector<unsigned char> syms, bits;
-    pairs.reserve(block); syms.reserve(2 * block); bits.resize(block);
+    std::vector<unsigned char> syms(2 * ((size_t)block + 2)), cmps(2 * ((size_t)block + 2)), bits(block + 2);
+    size_t npairs = 0;                   // pairs collected for the running block
     std::vector<unsigned char> inbuf(1 << 20);
     std::vector<char> outbuf;
+    long long tot_verified = 0, tot_redone = 0, tot_inner_verified = 0, tot_inner_redone = 0, tot_blocks = 0;
+    int worst_spread = 0;
 
     // per-pair state of the output side (vdecode.c:147-184)
     int startup = delay;
@@ -160,30 +150,44 @@ int main(int argc, char *argv[])
     };
 
     auto flush_block = [&]() -> int {
-        const int n = (int)pairs.size();
+        const int n = (int)npairs;
+        flip_at.clear();
+        for (unsigned long long f : flips_abs) flip_at.push_back((size_t)(f - pairs_before));
+        flips_abs.clear();
+        pairs_before += npairs;
+        npairs = 0;
         if (n == 0) {
-            for (size_t f = 0; f < flip_at.size(); f++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
-            flip_at.clear();
+            for (size_t f = 0; f < flip_at.size() && !quiet; f++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
             return 0;
         }
-        syms.resize(2 * (size_t)n);
-        for (int i = 0; i < n; i++) { syms[2 * i] = pairs[i].s0; syms[2 * i + 1] = pairs[i].s1; }
         if (pairs_only) {
-            fwrite(syms.data(), 1, syms.size(), stdout);
-            for (size_t f = 0; f < flip_at.size(); f++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
-            pairs.clear();
-            flip_at.clear();
+            fwrite(syms.data(), 1, 2 * (size_t)n, stdout);
+            for (size_t f = 0; f < flip_at.size() && !quiet; f++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
             return 0;
         }
-        bits.resize(n);
-        if (v224x_stream_decode_seg(vd, syms.data(), n, delay, bits.data(), nseg, -1, nullptr) < 0) {
-            fprintf(stderr, "%s: decode failed: %s\n", argv[0], v224x_last_error());
-            return -1;
+        if (vm) {
+            v224x_multi_report rep;
+            if (v224x_multi_stream_decode(vm, syms.data(), n, delay, bits.data(), nseg, -1, &rep) < 0) {
+                fprintf(stderr, "%s: decode failed: %s\n", argv[0], v224x_last_error());
+                return -1;
+            }
+            tot_verified += rep.handovers_verified; tot_redone += rep.ranges_redone;
+            tot_inner_verified += rep.inner_verified; tot_inner_redone += rep.inner_redone;
+            if (rep.worst_spread > worst_spread) worst_spread = rep.worst_spread;
+        } else {
+            v224x_seg_report rep;
+            if (v224x_stream_decode_seg(vd, syms.data(), n, delay, bits.data(), nseg, -1, &rep) < 0) {
+                fprintf(stderr, "%s: decode failed: %s\n", argv[0], v224x_last_error());
+                return -1;
+            }
+            tot_inner_verified += rep.verified; tot_inner_redone += rep.redone;
+            if (rep.worst_spread > worst_spread) worst_spread = rep.worst_spread;
         }
+        tot_blocks++;
         outbuf.clear();
         size_t nf = 0;
         for (int i = 0; i < n; i++) {
-            while (nf < flip_at.size() && flip_at[nf] == (size_t)i) { fprintf(stderr, "%s: flipping phase\n", argv[0]); nf++; }
+            while (nf < flip_at.size() && flip_at[nf] == (size_t)i) { if (!quiet) fprintf(stderr, "%s: flipping phase\n", argv[0]); nf++; }
             if (startup == 0) {
                 const int bit = bits[i];
                 if (framing) frame_bit(bit);
@@ -193,18 +197,16 @@ int main(int argc, char *argv[])
                 startup--;
             }
             const int e1 = G1FLIP ^ parity64(re_encoder & POLY1), e2 = G2FLIP ^ parity64(re_encoder & POLY2);
-            if (startup == 0) symerrs += (unsigned long long)((e1 ^ pairs[i].c1) + (e2 ^ pairs[i].c2));
+            if (startup == 0) symerrs += (unsigned long long)((e1 ^ cmps[2 * i]) + (e2 ^ cmps[2 * i + 1]));
             if (!quiet && interval != 0 && (++nbits % (unsigned long long)interval) == 0) {
                 fprintf(stderr, "%s: bits %'llu; symerrs %'llu/%'d %'.3lg%%\n", argv[0], nbits, symerrs, 2 * interval,
                         100. * symerrs / (2. * interval));
                 symerrs = 0;
             }
         }
-        for (; nf < flip_at.size(); nf++) fprintf(stderr, "%s: flipping phase\n", argv[0]);
+        for (; nf < flip_at.size(); nf++) if (!quiet) fprintf(stderr, "%s: flipping phase\n", argv[0]);
         if (!outbuf.empty()) fwrite(outbuf.data(), 1, outbuf.size(), stdout);
         fflush(stdout);
-        pairs.clear();
-        flip_at.clear();
         return 0;
     };
 
@@ -219,46 +221,22 @@ int main(int argc, char *argv[])
     for (;;) {
         const ssize_t got = read_some(inbuf.data(), inbuf.size());
         if (got <= 0) break;
-        for (ssize_t p = 0; p < got; p++) {
-            const unsigned char c = inbuf[p];
-            hist[slot] = c;
-            if ((slot & 1) == 0) even_sym = c;
-            if (!dontflip) {
-                // correlate the newest 34 symbols with the encoded sync pattern
-                int sum = 0;
-                for (int k = 0; k < NTAPS; k++) {
-                    const int v = (int)hist[(RING + slot + k - (NTAPS - 1)) % RING] - 128;
-                    sum += taps[k] ? v : -v;
-                }
-                if ((slot & 1) == 0) {
-                    if (sum > peak_out) peak_out = sum;
-                } else {
-                    if (sum > peak_in) peak_in = sum;
-                    if (++frame_count >= FRAME_SYMBOLS) {
-                        // once per frame: did the other symbol phase see the stronger sync?
-                        frame_count = 0;
-                        if (peak_out > peak_in) {
-                            if (!quiet) flip_at.push_back(pairs.size());     // the notice is printed where vdecode prints it
-                            slot += (slot & 1) ? -1 : 1;          // this symbol is not decoded; the next one reuses its slot
-                        }
-                        peak_in = peak_out = -1000000;
-                    }
-                }
-            }
-            if (slot & 1) {
-                PairRec r;
-                r.s0 = even_sym; r.s1 = c;
-                // (for delays beyond 2035 the reference's index goes negative -- undefined there; wrapped here)
-                r.c1 = hist[(((slot - back - 1) % RING) + RING) % RING] > 128;
-                r.c2 = hist[(((slot - back) % RING) + RING) % RING] > 128;
-                pairs.push_back(r);
-                if ((long)pairs.size() >= block && flush_block()) return 1;
-            }
-            slot = (slot + 1) % RING;
+        for (ssize_t p = 0; p < got;) {
+            // n symbols give at most n / 2 + 1 pairs: never more than the block has room for
+            const size_t room = (size_t)block - npairs;
+            const size_t take = std::min((size_t)(got - p), room > 1 ? 2 * (room - 1) : (size_t)1);
+            npairs += pairer.feed(inbuf.data() + p, take, syms.data() + 2 * npairs, cmps.data() + 2 * npairs, &flips_abs);
+            p += (ssize_t)take;
+            if ((long)npairs >= block && flush_block()) return 1;
         }
     }
     if (flush_block()) return 1;
     fflush(stdout);
+    if (verbose)
+        fprintf(stderr, "%s: %lld blocks on %d GPU(s); GPU-to-GPU hand-overs verified %lld, ranges redone %lld; lockstep hand-overs verified %lld, "
+                "segments redone %lld; worst snapshot spread %d; residual differences vs the sequential decode: 0 (by construction)\n",
+                argv[0], tot_blocks, ngpu, tot_verified, tot_redone, tot_inner_verified, tot_inner_redone, worst_spread);
+    if (vm) v224x_multi_delete(vm);
     delete_viterbi224(vd);
     return 0;
 }
