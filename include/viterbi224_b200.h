@@ -126,7 +126,7 @@ int v224x_metric_spread_dev(void *p, const void *dev_a, const void *dev_b, int *
 size_t v224x_snapshot_bytes(void);
 
 /* The same inside one process: one host thread and one CUDA stream per GPU, snapshots moved with peer copies.
- * devices[ngpu] = CUDA device ordinals (NULL: 0 .. ngpu-1); ring_rows = decision-ring rows per decoder (> delay; the
+ * devices[ngpu] = CUDA device ordinals (NULL: 0 .. ngpu-1; an ordinal listed twice makes two ranges share that GPU); ring_rows = decision-ring rows per decoder (> delay; the
  * stream is worked through in chunks of ring_rows - delay stages).  The context owns one decoder per GPU (plus the
  * lockstep partners of nseg > 1) and keeps the stream's state between calls: v224x_multi_init = init_viterbi224 for the
  * stream, every v224x_multi_stream_decode call continues where the last one ended (block-wise callers such as

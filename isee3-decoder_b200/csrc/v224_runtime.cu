@@ -1209,7 +1209,7 @@ void v224x_multi_delete(v224x_multi *m)
 v224x_multi *v224x_multi_create(const int *devices, int ngpu, int ring_rows)
 {
     const int ndev = v224x_device_count();
-    if (ngpu < 1 || ngpu > MULTI_MAX || ngpu > ndev) { set_err("v224x_multi_create: %d GPUs asked for, %d visible (1..%d supported)", ngpu, ndev, MULTI_MAX); return nullptr; }
+    if (ngpu < 1 || ngpu > MULTI_MAX || ndev < 1 || (!devices && ngpu > ndev)) { set_err("v224x_multi_create: %d GPUs asked for, %d visible (1..%d supported)", ngpu, ndev, MULTI_MAX); return nullptr; }
     v224x_multi *m = static_cast<v224x_multi *>(calloc(1, sizeof(v224x_multi)));
     if (!m) return nullptr;
     m->n = ngpu;
@@ -1217,9 +1217,9 @@ v224x_multi *v224x_multi_create(const int *devices, int ngpu, int ring_rows)
     const int saved = g_device;
     for (int k = 0; k < ngpu; k++) {
         m->devs[k] = devices ? devices[k] : k;
+        // (a device may be listed more than once: its ranges then share the GPU -- how the one-GPU test tier runs this code)
         bool ok = m->devs[k] >= 0 && m->devs[k] < ndev;
-        for (int t = 0; t < k; t++) ok = ok && m->devs[t] != m->devs[k];
-        if (!ok) { set_err("v224x_multi_create: bad or repeated device %d", m->devs[k]); g_device = saved; v224x_multi_delete(m); return nullptr; }
+        if (!ok) { set_err("v224x_multi_create: bad device %d", m->devs[k]); g_device = saved; v224x_multi_delete(m); return nullptr; }
         g_device = m->devs[k];
         m->dec[k] = static_cast<Decoder *>(create_viterbi224(ring_rows));
         ok = m->dec[k] != nullptr;

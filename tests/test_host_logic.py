@@ -100,18 +100,44 @@ def _free_port():
     return p
 
 
-def test_two_rank_segmented_decode_gloo(built):
-    """world_size 2 over gloo on CPU: partition, warm-up, gather.  The CPU oracle stands in for the GPU
-    decoder so that the host logic of the N>1 path is covered without a GPU."""
+@pytest.mark.parametrize("conv,expect", [(160, "verified=1 redone=0 spread=0"), (0, "verified=0 redone=1")])
+def test_two_rank_verified_segments_gloo(built, conv, expect):
+    """world_size 2 over gloo on CPU: segments.decode_verified -- ranges, snapshot exchange, hand-over check, and (conv = 0:
+    the check must fail) the exact redo of a range by the previous rank.  The CPU oracle stands in for the GPU decoder
+    so that the host protocol of the N>1 path is covered without a GPU; the stitched output equals one sequential decode."""
     port = _free_port()
     procs = []
     for rank in range(2):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_segment_worker.py")], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_segment_worker.py"), str(conv)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
-    assert "RESULT diff=0 data_ok=True n=144" in outs[0], outs[0]
+    assert "RESULT diff=0 data_ok=True n=400" in outs[0] and expect in outs[0], outs[0]
+
+
+def test_library_pairing_equals_the_python_mirror(built):
+    """v224x_pair_symbols (the library's host-side entry, run-at-a-time correlation) against the Python mirror of
+    vdecode.c:101-140: pairs, comparison symbols of the re-encode tally, flip positions; both start phases, -F, streams
+    with junk prefixes and lost symbols at 3 .. -2 dB (false-alarm flips)."""
+    for seed, junk, ebn0, nb, drop in [(1, 101, 3.0, 40, []), (2, 0, 1.0, 24, []), (3, 7, 0.0, 20, [9_000]), (4, 1, -2.0, 48, [50_000, 90_001])]:
+        _, soft = S.telemetry_stream(nb * 1024, ebn0, seed=seed, junk_symbols=junk)
+        soft = np.delete(soft, drop)
+        for phase in (0, 1):
+            want, wflips = v224.vdecode.pair_symbols(soft, start_phase=phase, return_flips=True)
+            got, gflips, cmp_ = v224.pair_symbols(soft, start_phase=phase, delay=200, want_cmp=True)
+            fast, fflips = v224.pair_symbols(soft, start_phase=phase)
+            assert np.array_equal(got, want) and np.array_equal(fast, want) and gflips == fflips and len(gflips) == len(wflips)
+            # comparison symbols: the hard-sliced history 2 * (delay + 22) symbols back, i.e. the pair 222 pairs earlier
+            # (exact only while no flip lies in between; checked on the flip-free case)
+            if not gflips and phase == 0:
+                k = np.arange(300, got.shape[0])
+                assert np.array_equal(cmp_[k], (got[k - 222] > 128).astype(np.uint8))
+        want = v224.vdecode.pair_symbols(soft, dontflip=True)
+        got, gflips = v224.pair_symbols(soft, dontflip=True)
+        assert np.array_equal(got, want) and gflips == []
+    assert v224.pair_symbols(np.zeros(0, np.uint8))[0].shape == (0, 2)
+    assert v224.pair_symbols(np.array([7], np.uint8))[0].shape == (0, 2)
 
 
 def test_block_driver_pairing_equals_the_python_mirror(built):
