@@ -9,7 +9,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libviterbi224_b200.so")
 # (source, extra nvcc flags).  The fused ACS pass is compiled with ptxas -O1: at the default level ptxas reorders the
 # decision-bit gather behind a whole stage of butterflies and spills; in source order the tile body needs no spill.
-SOURCES = [("v224_acs_persist.cu", ["-Xptxas", "-O1"]), ("v224_kernels.cu", []), ("v224_runtime.cu", [])]
+# The fused pass is built twice: 64-column tiles (lockstep decoders) and 32-column tiles (a decoder running alone).
+SOURCES = [("v224_acs_persist.cu", ["-Xptxas", "-O1"], "v224_acs_persist.o"),
+           ("v224_acs_persist.cu", ["-Xptxas", "-O1", "-DV224_TILE_COLS_LOG2=5", "-DV224_NS=v224t32"], "v224_acs_persist_t32.o"),
+           ("v224_kernels.cu", [], "v224_kernels.o"), ("v224_runtime.cu", [], "v224_runtime.o")]
 HOST_SOURCES = ["v224_pairing.cpp"]           # plain C++ (g++ -O3): host-side entries of the library, no CUDA
 HEADERS = ["v224_common.cuh", "v224_fused_core.cuh", "v224_kernels.h", "v224_pairing.cpp", os.path.join("..", "host", "pairing.h"),
            os.path.join("..", "..", "include", "viterbi224.h"), os.path.join("..", "..", "include", "viterbi224_b200.h")]
@@ -62,8 +65,8 @@ def build_library(force=False, verbose=False, out=None, extra_flags=()):
     nvcc = nvcc_path()
     objs = []
     log = []
-    for s, flags in SOURCES:
-        o = (out + "." if variant else os.path.join(CSRC, "")) + s.replace(".cu", ".o")
+    for s, flags, oname in SOURCES:
+        o = (out + "." if variant else os.path.join(CSRC, "")) + oname
         cmd = [nvcc, *NVCC_FLAGS, *flags, *extra_flags, "-c", "-o", o, os.path.join(CSRC, s)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)

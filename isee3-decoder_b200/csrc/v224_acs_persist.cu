@@ -21,7 +21,7 @@
 #include <mutex>
 #include <cuda.h>          // CUtensorMap and the cuTensorMapEncodeTiled prototype only; the entry point is fetched at run time
 
-namespace v224 {
+namespace V224_NS {
 
 #ifdef V224_TRACE
 // per (pass < 64, decoder < 4, tile < 512): 8 event timestamps (globaltimer ns) + the SM the tile ran on
@@ -139,7 +139,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
-// one tile = one 2-D tensor copy: box 64 columns x 256 rows at column x0 (TMA engine; bytes counted on the mbarrier)
+// one tile = one 2-D tensor copy: box FUSED_TILE_COLS columns x 256 rows at column x0 (TMA engine; bytes counted on the mbarrier)
 __device__ __forceinline__ void tma_load_tile(void *smem_dst, const void *tmap, int x0, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PASSTAB_WORDS) k_build_passtab(uint32_t *tab, 
         const int t = e - OPTAB_WORDS;
         const long long stage = (long long)pass * FK + t;
         v = (uint32_t)((T0 + stage) % len);
-        if (stage + len >= (long long)npasses * FK) row_fmt[v] = (uint8_t)(t + 1);
+        if (stage + len >= (long long)npasses * FK) row_fmt[v] = (uint8_t)(ROWFMT_FUSED_BASE + t + 1);
     }
     tab[(size_t)pass * PASSTAB_WORDS + e] = v;
 }
@@ -229,14 +229,7 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t labe
     }
 }
 
-// shared-memory exchange element (row m, column group g): NQ words.  For NQ = 2 a half-warp of round 2 reads two
-// rows 16 apart (same banks): swap the 64-byte halves of the odd-mh rows so that the two rows land on disjoint banks.
-__device__ __forceinline__ uint32_t xchg_index(uint32_t m, uint32_t g)
-{
-    return NQ == 2 ? m * FUSED_COLGROUPS + (g ^ ((m >> 1) & 8u)) : m * FUSED_COLGROUPS + g;
-}
-
-// Tile `tau` = columns [64 tau, 64 tau + 64) of all 256 rows.  Metrics are read through L2 only (another SM wrote
+// Tile `tau` = columns [FUSED_TILE_COLS tau, FUSED_TILE_COLS (tau + 1)) of all 256 rows.  Metrics are read through L2 only (another SM wrote
 // them, possibly within this launch).  `xbuf` = this tile's exchange buffer.
 template <bool CAREFUL>
 __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, uint32_t *s0, const TileInfo &ti, uint64_t *freeb, uint32_t labthr,
@@ -480,7 +473,17 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
         item = __shfl_sync(0xffffffffu, item, 0);
         const int n = (int)(item / per_pass);
         const unsigned r = item % per_pass, w = r % FUSED_TILES, s = r / FUSED_TILES;
+#if defined(V224_ORDER_DIAG) && V224_TILE_COLS_LOG2 == 5
+        // A/B: subgroups (h = tile >> 8, p = tile & 3) in anti-diagonal order h + p instead of class by class
+        uint32_t tau;
+        {
+            constexpr unsigned char HP[16][2] = {{0,0},{0,1},{1,0},{0,2},{1,1},{2,0},{0,3},{1,2},{2,1},{3,0},{1,3},{2,2},{3,1},{2,3},{3,2},{3,3}};
+            const unsigned sg = w >> 6, i = w & 63u;
+            tau = HP[sg][0] * 256u + i * 4u + HP[sg][1];
+        }
+#else
         const uint32_t tau = (w % 256u) * TILE_CLASSES + w / 256u;          // a pass emits its tile classes in turn
+#endif
         if (n >= m.npasses) {
             // no more work: tell the compute warps and the retirer
             if (lane == 0) sm.info[b].go = -1;
@@ -508,11 +511,11 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
             const int stop = (int)(unsigned)__shfl_sync(0xffffffffu, v, 1);
             const unsigned long long dwd = __shfl_sync(0xffffffffu, v, 2);
             stopped = n >= stop;
-            // tile tau reads only the 256 tiles == (tau >> 8) mod TILE_CLASSES of the previous pass
+            // tile tau reads only the 256 tiles of class tau >> 8 (== tile index mod TILE_CLASSES) of the previous pass
             // (the slots are recycled every PSLOTS passes: the done word carries the pass it counts for, so a stale word of
             // pass n - 1 - PSLOTS can never read as "complete")
             const bool ready = (unsigned)(pw >> 32) == (unsigned)(n + 1) &&
-                               (n == 0 || (done_word_pass(dwd) == (unsigned)((n - 1) & 0xffff) && done_class_count(dwd, tau >> 8) >= 256u));
+                               (n == 0 || (done_word_pass(dwd) == done_word_pass(done_word_fresh(n - 1)) && done_class_count(dwd, tau >> 8) >= 256u));
             if (stopped || ready) break;
             if (spins > SPIN_LIMIT) {            // a wait that lasts seconds means a broken invariant: flag it, never hang the GPU
                 if (lane == 0) { atomicOr((unsigned *)&a.ctl->error, 16u); atomicMin(&pc.stop_pass, 0); }
@@ -542,9 +545,9 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
         __syncwarp();
         if (lane == 0) {
             if (BULK_LOAD && !stopped) {
-                // pass table (1 KiB) and tile (256 rows x 128 bytes, rows 64 KiB apart, one tensor copy) -> shared memory;
+                // pass table (1 KiB) and tile (256 rows x 2 * FUSED_TILE_COLS bytes, rows 64 KiB apart, one tensor copy) -> shared memory;
                 // the hand-over completes when the bytes have landed
-                mbar_arrive_expect_tx(&sm.full[b], 256u * 128u + PASSTAB_WORDS * 4u);
+                mbar_arrive_expect_tx(&sm.full[b], 256u * FUSED_TILE_COLS * 2u + PASSTAB_WORDS * 4u);
                 bulk_g2s(sm.tab[b], a.passtab + (size_t)n * PASSTAB_WORDS, PASSTAB_WORDS * 4u, &sm.full[b]);
                 tma_load_tile(sm.tile[k & 1], reinterpret_cast<const uint8_t *>(a.tmaps) + (size_t)cur * TMAP_BYTES, (int)(tau * FUSED_TILE_COLS), &sm.full[b]);
             } else {
@@ -668,7 +671,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     // per-device launch geometry, looked up once; callers may come from several host threads (one per GPU)
     constexpr int MAXDEV = 64;
     static std::mutex mu;
-    static int checked[MAXDEV], slots[MAXDEV];
+    static int checked[MAXDEV], slots[MAXDEV], sm_count[MAXDEV];
     if (dev < 0 || dev >= MAXDEV) return cudaErrorInvalidDevice;
     int nslots = 0;
     {
@@ -683,11 +686,13 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
             e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
             slots[dev] = per_sm * sms;
+            sm_count[dev] = sms;
             checked[dev] = 1;
         }
         nslots = slots[dev];
     }
     if (m.grid_limit > 0 && m.grid_limit < nslots) nslots = m.grid_limit;
+    if (m.grid_limit < 0 && -m.grid_limit * sm_count[dev] < nslots) nslots = -m.grid_limit * sm_count[dev];          // that many CTAs per SM
     for (int s = 0; s < m.nctx; s++) {
         const PersistArgs &a = m.ctx[s];
         k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
@@ -699,15 +704,28 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     return cudaGetLastError();
 }
 
-} // namespace v224
+} // namespace V224_NS
+
+#if V224_TILE_COLS_LOG2 == 5
+// The 32-column build is reached from the runtime (compiled against the 64-column headers) through these two entries; the
+// argument structures have the same layout in both namespaces (nothing in them depends on the tile width).
+extern "C" cudaError_t v224_t32_launch_persist(const void *multi_args, cudaStream_t st)
+{
+    return V224_NS::launch_persist(*static_cast<const V224_NS::MultiArgs *>(multi_args), st);
+}
+extern "C" cudaError_t v224_t32_build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why)
+{
+    return V224_NS::build_metric_tensor_maps(metrics, dev_out, st, why);
+}
+#endif
 
 #ifdef V224_TRACE
 extern "C" int v224_debug_read_trace(unsigned long long *host, unsigned long long n)
 {
-    return (int)cudaMemcpyFromSymbol(host, v224::g_trace, n * sizeof(unsigned long long));
+    return (int)cudaMemcpyFromSymbol(host, V224_NS::g_trace, n * sizeof(unsigned long long));
 }
 extern "C" int v224_debug_read_smid(unsigned *host, unsigned long long n)
 {
-    return (int)cudaMemcpyFromSymbol(host, v224::g_smid, n * sizeof(unsigned));
+    return (int)cudaMemcpyFromSymbol(host, V224_NS::g_smid, n * sizeof(unsigned));
 }
 #endif

@@ -6,7 +6,18 @@
 #include <cstddef>
 #include <cuda_runtime.h>
 
-namespace v224 {
+// The fused-pass translation unit is compiled twice: tiles of 64 columns (namespace v224, the lockstep multi-decoder shape)
+// and tiles of 32 columns (-DV224_TILE_COLS_LOG2=5 -DV224_NS=v224t32: twice as many tiles of half the latency and a quarter
+// instead of half of the previous pass as each tile's dependency -- the shape a decoder running alone wants).  Everything
+// that depends on the tile width lives in that unit's namespace; the two decision-row layouts are told apart by the row tag.
+#ifndef V224_NS
+#define V224_NS v224
+#endif
+#ifndef V224_TILE_COLS_LOG2
+#define V224_TILE_COLS_LOG2 6
+#endif
+
+namespace V224_NS {
 
 constexpr int      K        = 24;                  // code.h:61
 constexpr uint32_t POLY1    = 073665667u;          // code.h:59
@@ -42,18 +53,19 @@ constexpr int NQ = V224_NQ;                        // packed 2x16-bit registers 
 static_assert(NQ == 2 || NQ == 4, "columns per thread");
 constexpr int COLW_LOG2 = NQ == 2 ? 2 : 3;         // log2(columns per thread)
 constexpr int COLW = 1 << COLW_LOG2;
-constexpr int FUSED_COLS_LOG2 = 6;
+constexpr int FUSED_COLS_LOG2 = V224_TILE_COLS_LOG2;
+static_assert(FUSED_COLS_LOG2 == 6 || FUSED_COLS_LOG2 == 5, "tile width");
 constexpr int FUSED_TILE_COLS = 1 << FUSED_COLS_LOG2;  // columns (j) per tile
 constexpr int FUSED_COLGROUPS = FUSED_TILE_COLS / COLW; // column groups (one per thread column) per tile: 16 / 8
 constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column groups: 256 / 128
 // CTA = FUSED_THREADS compute threads + one protocol warp (v224_acs_persist.cu).  3 CTAs of 288 threads per SM at 72
 // registers; the round-1 -> round-2 exchange buffer is double-buffered when shared memory allows (3 x 67 KiB).
 #ifndef V224_CTAS_PER_SM
-#define V224_CTAS_PER_SM 3
+#define V224_CTAS_PER_SM (V224_TILE_COLS_LOG2 == 6 ? 3 : 5)
 #endif
 constexpr int FUSED_CTAS_PER_SM = V224_CTAS_PER_SM;
 #ifndef V224_XCHG_BUFS
-#define V224_XCHG_BUFS (V224_CTAS_PER_SM <= 3 ? 2 : 1)
+#define V224_XCHG_BUFS ((V224_CTAS_PER_SM <= 3 || V224_TILE_COLS_LOG2 == 5) ? 2 : 1)
 #endif
 constexpr int XCHG_BUFS = V224_XCHG_BUFS;
 // The protocol warp prefetches a tile's input into its exchange buffer with bulk asynchronous copies (TMA engine)
@@ -64,7 +76,7 @@ constexpr int XCHG_BUFS = V224_XCHG_BUFS;
 constexpr bool BULK_LOAD = V224_BULK_LOAD;
 static_assert(!BULK_LOAD || XCHG_BUFS == 2, "bulk prefetch needs the double exchange buffer");
 constexpr int FUSED_TILES     = (1 << (23 - FK)) / FUSED_TILE_COLS;   // 512 tiles per pass
-constexpr int TILE_CLASSES    = 128 / FUSED_TILE_COLS; // tile t of pass n+1 reads the tiles == (t >> 8) mod TILE_CLASSES of pass n
+constexpr int TILE_CLASSES    = 128 / FUSED_TILE_COLS; // tile t of pass n+1 reads the 256 tiles == (t >> 8) mod TILE_CLASSES of pass n
 
 // Path-metric buffers rotate A -> B -> C -> A.  Three (not two) so that, in the persistent kernel,
 // pass n+1 may already be writing while pass n is still being validated: pass n's input stays
@@ -73,9 +85,11 @@ constexpr int NBUF = 3;
 constexpr int PSLOTS = 4;                          // in-flight pass bookkeeping slots (ring)
 
 // Decision-row formats (row_fmt[] tags).  0 = canonical (bit index = new-state number, the
-// reference's layout, viterbi224_sse2.c:141,324); other values = written by a stage of a fused
-// pass in that kernel's thread-major layout (see fused_bit_address()).
+// reference's layout, viterbi224_sse2.c:141,324); 1..8 = written by stage t of a fused pass with 64-column tiles,
+// 9..16 = by stage t - 8 of a fused pass with 32-column tiles, each in that kernel's thread-major layout
+// (see fused_bit_address()).
 constexpr uint8_t ROWFMT_CANON = 0;
+constexpr uint8_t ROWFMT_FUSED_BASE = FUSED_COLS_LOG2 == 6 ? 0 : 8;    // tag of stage t = base + t
 
 // Device-resident control block.  One per decoder handle.  The last CTA of every pass
 // ("resolver") folds the pass's statistics into it; the host only reads it back at the end of
@@ -116,8 +130,8 @@ __host__ __device__ inline unsigned stats_max(const PassStats &s)
 
 // Bookkeeping of one in-flight pass of the persistent kernel.  Two 64-bit words carry everything a tile's protocol
 // warp has to poll, so that one round of parallel loads decides "may this tile start":
-//   done_word = [63:48] class-1 tiles done | [47:32] class-0 tiles done | [31:16] pass number mod 2^16 | [15:0] tiles done
-//               (class = tile index mod 2; the pass tag is written when the slot is reset for that pass)
+//   done_word = [63:24] tiles done per class, 10 bits each (class = tile index mod TILE_CLASSES) | [23:11] pass number mod 2^13
+//               | [10:0] tiles done      (the pass tag is written when the slot is reset for that pass)
 //   pass_word = (pass number + 1) << 32 | careful << 31 | sub     published by the resolver of pass n-2 (or the launch)
 struct PassSlot {
     PassStats st;
@@ -128,12 +142,12 @@ __host__ __device__ inline unsigned long long make_pass_word(int n, int careful,
 {
     return ((unsigned long long)(unsigned)(n + 1) << 32) | ((unsigned long long)(careful ? 1u : 0u) << 31) | (unsigned)sub;
 }
-__host__ __device__ inline unsigned done_class_count(unsigned long long w, unsigned cls) { return (unsigned)(w >> (32 + 16 * cls)) & 0xffffu; }
-__host__ __device__ inline unsigned long long done_increment(unsigned cls) { return 1ull | (1ull << (32 + 16 * cls)); }
-__host__ __device__ inline unsigned long long done_word_fresh(int pass) { return (unsigned long long)((unsigned)pass & 0xffffu) << 16; }
-__host__ __device__ inline unsigned done_word_pass(unsigned long long w) { return (unsigned)(w >> 16) & 0xffffu; }
-__host__ __device__ inline unsigned done_total(unsigned long long w) { return (unsigned)w & 0xffffu; }
-static_assert(TILE_CLASSES == 2, "done_word layout");
+__host__ __device__ inline unsigned done_class_count(unsigned long long w, unsigned cls) { return (unsigned)(w >> (24 + 10 * cls)) & 0x3ffu; }
+__host__ __device__ inline unsigned long long done_increment(unsigned cls) { return 1ull | (1ull << (24 + 10 * cls)); }
+__host__ __device__ inline unsigned long long done_word_fresh(int pass) { return (unsigned long long)((unsigned)pass & 0x1fffu) << 11; }
+__host__ __device__ inline unsigned done_word_pass(unsigned long long w) { return (unsigned)(w >> 11) & 0x1fffu; }
+__host__ __device__ inline unsigned done_total(unsigned long long w) { return (unsigned)w & 0x7ffu; }
+static_assert(TILE_CLASSES <= 4 && FUSED_TILES <= 1024, "done_word layout");
 struct PersistCtl {
     unsigned next_item;     // dynamic work queue head: item = pass * 512 + order index
     unsigned resolved_upto; // number of passes resolved (in order)
@@ -164,6 +178,8 @@ struct Ctl {
     // ---- everything above is what the host mirrors after each call (CTL_HOST_BYTES) ----
     PassStats st;           // statistics of the running per-pass / single-stage kernel, reset by its resolver
     PersistCtl pc;
+    unsigned spec_first;    // per-bit streaming: (stage counter after the stage) << 1 | first decision of the speculative decodebit walk
+    unsigned pad1;
 };
 constexpr size_t CTL_HOST_BYTES = offsetof(Ctl, st);
 
@@ -182,37 +198,51 @@ __host__ __device__ inline void round2_map(uint32_t tid, uint32_t &thr, uint32_t
     thr = (w / (FUSED_COLGROUPS / 8)) * 4 + (lane >> 3);
     g = (w % (FUSED_COLGROUPS / 8)) * 8 + (lane & 7);
 }
-__host__ __device__ inline uint32_t round2_tid(uint32_t thr, uint32_t g)
+__host__ __device__ inline uint32_t round2_tid_cg(uint32_t thr, uint32_t g, uint32_t colgroups)
 {
-    const uint32_t w = (thr >> 2) * (FUSED_COLGROUPS / 8) + (g >> 3), lane = ((thr & 3) << 3) | (g & 7);
+    const uint32_t w = (thr >> 2) * (colgroups / 8) + (g >> 3), lane = ((thr & 3) << 3) | (g & 7);
     return (w << 5) | lane;
 }
+__host__ __device__ inline uint32_t round2_tid(uint32_t thr, uint32_t g) { return round2_tid_cg(thr, g, FUSED_COLGROUPS); }
 
-// Decision-row formats: 0 = canonical; t (1..8) = written by stage t of a fused pass.  Fused rows hold the COMPLEMENT of
-// the decision bit (the sign bit the butterfly produces is the inverted decision; flipping it once per traceback read
-// is cheaper than once per state update).
+// shared-memory exchange element (row m, column group g) between the two register rounds, in units of NQ words.  A
+// half-warp of round 2 reads rows 16 apart (same banks): 64-column tiles swap the 64-byte halves of the rows with odd
+// mh bit 1 position, 32-column tiles (64-byte rows) swap neighbouring rows of odd mh -- either way the rows a warp reads
+// together land on disjoint banks, and a round-1 thread still writes exactly the rows its own warp read (in place).
+__host__ __device__ inline uint32_t xchg_index(uint32_t m, uint32_t g)
+{
+    if (NQ != 2) return m * FUSED_COLGROUPS + g;
+    if (FUSED_COLGROUPS == 16) return m * FUSED_COLGROUPS + (g ^ ((m >> 1) & 8u));
+    return (m ^ ((m >> 4) & 1u)) * FUSED_COLGROUPS + g;
+}
+
+// Decision-row formats: 0 = canonical; otherwise written by stage t of a fused pass (tag = t for 64-column tiles, 8 + t
+// for 32-column tiles).  Fused rows hold the COMPLEMENT of the decision bit (the sign bit the butterfly produces is the
+// inverted decision; flipping it once per traceback read is cheaper than once per state update).
 constexpr uint32_t FUSED_ROWS_COMPLEMENTED = 1u;
 // Where a fused-format decision bit lives: state s after stage t -> bit index inside the 2^23-bit row.
-// Slot fields (23 bits): mh[4] | ml[4] | j[15], j = tile[9] | g | q | h.  The thread (tile, tid) owns the NQ
-// consecutive words starting at word (tile * FUSED_THREADS + tid) * NQ; inside them
+// Slot fields (23 bits): mh[4] | ml[4] | j[15], j = tile | g | q | h.  The thread (tile, tid) owns the NQ
+// consecutive words starting at word (tile * threads + tid) * NQ; inside them
 //   word = side * NQ/2 + q/2, byte = (q & 1) * 2 + h, bit = pair index
 // where `inner` is the 4-bit row index a thread holds in that round (mh in round 1, ml in round 2), the stage's
 // butterfly pairs the two rows that differ in bit sb of `inner`, side = that bit, pair index = the other three.
 __host__ __device__ inline uint32_t fused_bit_address(int fmt, uint32_t s)
 {
-    const int t = fmt;
+    const int cols_log2 = fmt > 8 ? 5 : 6;
+    const int t = fmt > 8 ? fmt - 8 : fmt;
+    const uint32_t colgroups = (1u << cols_log2) / COLW, threads = 16 * colgroups;
     uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;      // the slot its survivor sits in during the pass
     const uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, j = p & 32767;
-    const uint32_t tile = j >> FUSED_COLS_LOG2, g = (j & (FUSED_TILE_COLS - 1)) >> COLW_LOG2;
+    const uint32_t tile = j >> cols_log2, g = (j & ((1u << cols_log2) - 1)) >> COLW_LOG2;
     const uint32_t q = (j & (COLW - 1)) >> 1, h = j & 1;
     const bool r1 = t <= FR;
     const uint32_t inner = r1 ? mh : ml;
-    const uint32_t tid = r1 ? ml * FUSED_COLGROUPS + g : round2_tid(mh, g);
+    const uint32_t tid = r1 ? ml * colgroups + g : round2_tid_cg(mh, g, colgroups);
     const int sb = FR - 1 - ((t - 1) % FR);
     const uint32_t side = (inner >> sb) & 1;
     const uint32_t pidx = ((inner >> (sb + 1)) << sb) | (inner & ((1u << sb) - 1));
-    const uint32_t word = (tile * FUSED_THREADS + tid) * NQ + side * (NQ / 2) + (q >> 1);
+    const uint32_t word = (tile * threads + tid) * NQ + side * (NQ / 2) + (q >> 1);
     return word * 32 + (((q & 1) << 1) | h) * 8 + pidx;
 }
 
-} // namespace v224
+} // namespace V224_NS

@@ -28,7 +28,7 @@
 
 #if defined(V224_HOST_EMU) && !defined(__CUDA_ARCH__)
 #define V224_HD
-namespace v224 {
+namespace V224_NS {
 static inline uint32_t f_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
 static inline uint32_t f_addmin_u16x2(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -63,7 +63,7 @@ static inline uint32_t f_maxu2(uint32_t a, uint32_t b)
 }
 #else
 #define V224_HD __device__ __forceinline__
-namespace v224 {
+namespace V224_NS {
 V224_HD uint32_t f_popc(uint32_t x) { return (uint32_t)__popc(x); }
 V224_HD uint32_t f_addmin_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }   // VIADDMNMX.U16x2
 // PRMT in its default mode: bit 3 of a selector nibble replicates the selected byte's sign bit.
@@ -79,7 +79,7 @@ V224_HD uint32_t f_maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 }
 #endif
 
-namespace v224 {
+namespace V224_NS {
 
 // Slot-bit mask of POLY at stage t (1-based): slot bit s feeds register bit ((s+t-1) mod 23)+1.
 __host__ __device__ constexpr uint32_t slotmask(uint32_t poly, int t)

@@ -14,6 +14,7 @@
 #include "v224_common.cuh"
 #include "v224_kernels.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace v224 {
 
@@ -82,8 +83,49 @@ __global__ void __launch_bounds__(256) k_init(uint16_t *m0, Ctl *c, uint32_t sta
         c->spread = bias;
         c->cur = 0;
         c->error = 0;
+        c->spec_first = 0;
         reset_stats(c);
     }
+}
+
+__device__ __forceinline__ uint32_t read_decision(const uint32_t *ring, const uint8_t *row_fmt, long long row, uint32_t state)
+{
+    const uint8_t f = row_fmt[row];
+    const uint32_t bit = f == ROWFMT_CANON ? state : fused_bit_address(f, state);
+    const uint32_t flip = f == ROWFMT_CANON ? 0u : FUSED_ROWS_COMPLEMENTED;
+    return ((ring[(size_t)row * ROWWORDS + (bit >> 5)] >> (bit & 31)) & 1u) ^ flip;     // viterbi224_sse2.c:141
+}
+
+// Incremental decodebit walk (see k_walk_incremental below): `delay` rows back from ring head T, stopping where the path
+// rejoins the previous call's (cached) path.  Returns the bit decodebit(delay, endstate) returns.
+// first_bit >= 0: the decision of (row T-1, endstate) is known to the caller (the one-stage kernel walks while the rest of
+// its grid is still writing that row) and is not read from the ring.
+// all_canon: the host knows that every row in the ring is in the canonical layout (no fused pass has written into it):
+// the row tags are not read, which halves the chain of dependent loads.
+__device__ int incremental_walk(const uint32_t *ring, const uint8_t *row_fmt, int len, long long T, long long prev_T, int delay, uint32_t endstate,
+                                uint32_t *cache, unsigned *steps_out, int first_bit = -1, bool all_canon = false)
+{
+    uint32_t st = endstate & STATEMASK;
+    int bit = -1;
+    unsigned steps = 0;
+    for (long long t = T - 1; t >= T - delay; t--) {
+        const long long row = ((t % len) + len) % len;
+        if (t == T - 1 && first_bit >= 0) bit = first_bit;
+        else if (all_canon) bit = (int)((__ldcg(ring + (size_t)row * ROWWORDS + (st >> 5)) >> (st & 31)) & 1u);      // viterbi224_sse2.c:141
+        else bit = (int)read_decision(ring, row_fmt, row, st);
+        st = ((uint32_t)bit << (K - 2)) | (st >> 1);
+        steps++;
+        const bool cached = t <= prev_T - 1 && t >= prev_T - delay && t > T - delay;
+        if (cached && cache[row] == st) {
+            // merged with the previous path: the state at time T - delay is the cached one
+            const long long r2 = (((T - delay) % len) + len) % len;
+            bit = (int)((cache[r2] >> (K - 2)) & 1u);
+            break;
+        }
+        cache[row] = st;
+    }
+    if (steps_out) atomicAdd(steps_out, steps);
+    return bit;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -94,8 +136,15 @@ template <bool SAT>
 __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
 {
     Ctl *c = a.ctl;
-    if (c->T != a.expected_T || c->error) return;
-    if (!SAT && (c->maxR + 510 > 32767 || c->spread > MAX_FAST_SPREAD)) return;   // reference could saturate: use the SAT variant
+    if (c->T != a.expected_T || c->error || (!SAT && (c->maxR + 510 > 32767 || c->spread > MAX_FAST_SPREAD))) {
+        // declined: stale stage counter, sticky error, or the reference could saturate (the host then uses the SAT variant)
+        if (a.mailbox && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.mailbox->declined = 1;
+            __threadfence_system();
+            a.mailbox->seq = a.seq;
+        }
+        return;
+    }
     const long long T0 = c->T;
     const int sub = c->sub;
     const long long O = c->O;
@@ -148,6 +197,14 @@ __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
     if ((threadIdx.x & 1) == 0)
         __stcs(a.ring + (size_t)row * ROWWORDS + gid / 2, dec | (other << 16));
 
+    // Per-bit streaming: the decodebit walk the caller is about to ask for (vdecode.c:152) starts at new state spec_end of
+    // THIS row and from there on only reads older rows: the thread that computed that decision walks now, while the rest
+    // of the grid is still working, and leaves the answer for the resolver to post.
+    if (a.mailbox && a.spec_walk && (a.spec_end >> 4) == gid) {
+        const int first = (int)((dec >> (a.spec_end & 15u)) & 1u);
+        a.mailbox->walk_bit = incremental_walk(a.ring, a.row_fmt, a.len, T0 + 1, a.spec_prev_T, a.spec_delay, a.spec_end, a.walk_cache, a.walk_steps, first);
+        __threadfence_system();
+    }
     const uint32_t wmn = __reduce_min_sync(0xffffffffu, (uint32_t)mn);
     const uint32_t wmx = __reduce_max_sync(0xffffffffu, (uint32_t)mx);
     __shared__ uint32_t s_mn[8], s_mx[8];
@@ -169,22 +226,195 @@ __global__ void __launch_bounds__(256) k_acs_single(SingleArgs a)
         __threadfence();
         if (SAT) c->n_sat++; else c->n_single++;
         resolve_pass(c, 1, true, SAT);
+        if (a.mailbox) {
+            // per-bit streaming: everything the host needs after this stage, in mapped host memory, sequence number last
+            // (the speculative walk's answer is already there: its thread wrote it before its block took a ticket)
+            if (!a.spec_walk) a.mailbox->walk_bit = -2;
+            const unsigned *src = reinterpret_cast<const unsigned *>(c);
+            unsigned *dst = reinterpret_cast<unsigned *>(a.mailbox->ctl_head);
+            for (unsigned i = 0; i < CTL_HOST_BYTES / 4; i++) dst[i] = src[i];
+            a.mailbox->declined = 0;
+            __threadfence_system();
+            a.mailbox->seq = a.seq;
+        }
     }
 }
 template __global__ void k_acs_single<false>(SingleArgs);
 template __global__ void k_acs_single<true>(SingleArgs);
 
 // ------------------------------------------------------------------------------------------
-// traceback
+// single stage, fast form: packed 2 x uint16 arithmetic, one wave, every SM the same number of bytes
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t read_decision(const uint32_t *ring, const uint8_t *row_fmt, long long row, uint32_t state)
+// Same stage as k_acs_single<false> (viterbi224_sse2.c:277-328), restructured for latency: this is the kernel behind the
+// per-bit ABI pattern (vdecode.c:145: update(1) per decoded bit), where one launch is all there is to hide latency in.
+//   * unit = 8 butterflies b0 .. b0+7 (two 16-byte loads, one 32-byte metric store, 16 decision bits); a block owns a
+//     contiguous range of units -- NUNITS / gridDim.x of them, the same for every SM -- and its threads go through it two
+//     units at a time with all four loads in flight before the first add
+//   * a register holds the metrics of two neighbouring butterflies; both halves run the butterfly with their own branch
+//     metric.  The expected symbols of butterfly b0 + e are parity(16 u & POLY) ^ parity(2 e & POLY) (:75-76; the two
+//     polynomials differ in register bit 1 only, which 16 u does not have): one population count per unit decides whether
+//     the unit uses the kernel's four packed branch metrics or their complements 510 - x (:293)
+//   * the block takes ONE ticket; 2 * SMs blocks instead of 2048
+// The metrics stay below 2^16 in every half (spread <= MAX_FAST_SPREAD, checked on entry), so packed adds cannot carry.
+constexpr uint32_t NUNITS = NBFLY / 8;            // 2^19
+constexpr int SINGLE_FAST_THREADS = 512;
+
+struct FastUnit { uint4 va, vc; uint32_t u; };
+
+__device__ __forceinline__ void fast_unit(const FastUnit &f, uint32_t sub2, const uint32_t (&X0)[4], uint16_t *newm, uint32_t *ring_row,
+                                          uint32_t &mnp, uint32_t &mxp, uint32_t &dec_out, uint32_t &n00)
 {
-    const uint8_t f = row_fmt[row];
-    const uint32_t bit = f == ROWFMT_CANON ? state : fused_bit_address(f, state);
-    const uint32_t flip = f == ROWFMT_CANON ? 0u : FUSED_ROWS_COMPLEMENTED;
-    return ((ring[(size_t)row * ROWWORDS + (bit >> 5)] >> (bit & 31)) & 1u) ^ flip;     // viterbi224_sse2.c:141
+    const uint32_t wa[4] = {f.va.x, f.va.y, f.va.z, f.va.w}, wc[4] = {f.vc.x, f.vc.y, f.vc.z, f.vc.w};
+    // expected symbols of the unit's first butterfly, linear part (flips are folded into X0)
+    const bool t = (__popc((16u * f.u) & POLY1) & 1u) != 0;
+    uint32_t out[8];
+    uint32_t dec = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t x0 = X0[i], y0 = 0x01fe01feu - x0;
+        const uint32_t X = t ? y0 : x0, Y = t ? x0 : y0;                  // :292-293
+        const uint32_t pa = wa[i] - sub2, pc = wc[i] - sub2;
+        const uint32_t m0 = pa + X, m1 = pc + Y, m2 = pa + Y, m3 = pc + X;  // :296-299
+        const uint32_t g0 = __vcmpgtu2(m0, m1), g1 = __vcmpgtu2(m2, m3);    // :316-317 strict
+        const uint32_t n0 = __vminu2(m0, m1), n1 = __vminu2(m2, m3);        // :319-320
+        // decision bits of butterflies 2i (low halves) and 2i+1 (high halves): d0 at bit 2e, d1 at bit 2e+1 (:324)
+        const uint32_t tt = (g0 & 0x00010001u) | ((g1 & 0x00010001u) << 1);
+        dec |= ((tt | (tt >> 14)) & 0xfu) << (4 * i);
+        out[2 * i] = __byte_perm(n0, n1, 0x5410);                            // states 2b, 2b+1 of butterfly 2i (:326-327)
+        out[2 * i + 1] = __byte_perm(n0, n1, 0x7632);                        // ... of butterfly 2i+1
+        mnp = __vminu2(mnp, __vminu2(n0, n1));
+        mxp = __vmaxu2(mxp, __vmaxu2(n0, n1));
+        if (i == 0) n00 = n0 & 0xffffu;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(newm) + (size_t)f.u * 2;
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    // 16 decision bits per unit; neighbouring lanes hold neighbouring units: pair them into 32-bit words
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, dec, 1);
+    if ((f.u & 1u) == 0) __stcs(ring_row + f.u / 2, dec | (other << 16));
+    dec_out = dec;
 }
 
+// Run by the thread that took the stage's last ticket: resolve the stage and, in per-bit streaming, post the report.
+__device__ void finish_single_fast(Ctl *c, const SingleArgs &a)
+{
+    __threadfence();
+    c->n_single++;
+    resolve_pass(c, 1, true, false);
+    if (a.mailbox) {
+        // (a speculative walk's answer is already there: the walker wrote it before it took its ticket)
+        if (!a.spec_walk) a.mailbox->walk_bit = -2;
+        const unsigned *src = reinterpret_cast<const unsigned *>(c);
+        unsigned *dst = reinterpret_cast<unsigned *>(a.mailbox->ctl_head);
+        for (unsigned i = 0; i < CTL_HOST_BYTES / 4; i++) dst[i] = src[i];
+        a.mailbox->declined = 0;
+        __threadfence_system();
+        a.mailbox->seq = a.seq;
+    }
+}
+
+__global__ void __launch_bounds__(SINGLE_FAST_THREADS, 2) k_acs_single_fast(SingleArgs a)
+{
+    Ctl *c = a.ctl;
+    if (c->T != a.expected_T || c->error || c->maxR + 510 > 32767 || c->spread > MAX_FAST_SPREAD) {
+        // declined: stale stage counter, sticky error, or the reference could saturate (the host then uses the SAT variant)
+        if (a.mailbox && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.mailbox->declined = 1;
+            __threadfence_system();
+            a.mailbox->seq = a.seq;
+        }
+        return;
+    }
+    const long long T0 = c->T;
+    if (blockIdx.x == gridDim.x - 1 && a.spec_walk) {
+        // Walker block (per-bit streaming): the decodebit walk the caller is about to ask for (vdecode.c:152) starts at new
+        // state spec_end of THIS row and from there on only reads older rows.  It waits for that one decision (the thread
+        // that computes it publishes it, tagged with the stage) and walks while the other blocks are still working.
+        if (threadIdx.x == 0) {
+            const unsigned want = (unsigned)(T0 + 1);
+            unsigned v = 0;
+            for (unsigned spins = 0; spins < 50u * 1000u * 1000u; spins++) {
+                v = *(volatile unsigned *)&c->spec_first;
+                if ((v >> 1) == (want & 0x7fffffffu)) break;
+            }
+            long long bit = -3;                                   // the decision never came: the host falls back to its own walk
+            if ((v >> 1) == (want & 0x7fffffffu))
+                bit = incremental_walk(a.ring, a.row_fmt, a.len, T0 + 1, a.spec_prev_T, a.spec_delay, a.spec_end, a.walk_cache, a.walk_steps,
+                                       (int)(v & 1u), a.all_canon != 0);
+            a.mailbox->walk_bit = bit;
+            __threadfence_system();
+            if (atomicAdd(&c->ticket, 1u) == gridDim.x - 1) finish_single_fast(c, a);     // the walk outlasted the stage
+        }
+        return;
+    }
+    const uint32_t nwork = gridDim.x - (a.spec_walk ? 1u : 0u);    // blocks that share the stage's units
+    const uint32_t sub2 = (uint32_t)c->sub * 0x10001u;
+    const uint16_t *oldm = a.metrics[c->cur];
+    uint16_t *newm = a.metrics[(c->cur + 1) % NBUF];
+    const int s0 = a.use_arg_syms ? a.sym0 : a.syms[2 * (size_t)a.expected_pos];
+    const int s1 = a.use_arg_syms ? a.sym1 : a.syms[2 * (size_t)a.expected_pos + 1];
+    const long long row = T0 % a.len;
+    uint32_t *ring_row = a.ring + (size_t)row * ROWWORDS;
+    // the four packed branch metrics of a unit whose linear label part is 0: butterflies (2i, 2i+1) in the halves
+    uint32_t X0[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t x[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t e = 2 * i + h;
+            const int e1 = G1FLIP ^ (__popc((2u * e) & POLY1) & 1), e2 = G2FLIP ^ (__popc((2u * e) & POLY2) & 1);   // :75-76
+            x[h] = (uint32_t)((e1 ? 255 - s0 : s0) + (e2 ? 255 - s1 : s1));
+        }
+        X0[i] = x[0] | (x[1] << 16);
+    }
+    // this block's units: warp-aligned, the same count (+-32) for every block
+    const uint32_t wu0 = (uint32_t)(((unsigned long long)blockIdx.x * (NUNITS / 32)) / nwork) * 32u;
+    const uint32_t wu1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * (NUNITS / 32)) / nwork) * 32u;
+    uint32_t mnp = 0xffffffffu, mxp = 0;
+    const uint4 *old4 = reinterpret_cast<const uint4 *>(oldm);
+    for (uint32_t base = wu0; base < wu1; base += 2 * SINGLE_FAST_THREADS) {
+        FastUnit f[2];
+        bool on[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            f[k].u = base + k * SINGLE_FAST_THREADS + threadIdx.x;
+            on[k] = f[k].u < wu1;                       // whole warps switch on and off together (the range is warp-aligned)
+            if (on[k]) { f[k].va = old4[f[k].u]; f[k].vc = old4[f[k].u + NUNITS]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!on[k]) continue;
+            uint32_t dec, n00;
+            fast_unit(f[k], sub2, X0, newm, ring_row, mnp, mxp, dec, n00);
+            if (f[k].u == 0) { c->st.s0[1] = n00; a.row_fmt[row] = ROWFMT_CANON; }
+            // per-bit streaming: the walk's first decision (new state spec_end of THIS row), for the walker block
+            if (a.spec_walk && (a.spec_end >> 4) == f[k].u)
+                *(volatile unsigned *)&c->spec_first = ((unsigned)(T0 + 1) << 1) | ((dec >> (a.spec_end & 15u)) & 1u);
+        }
+    }
+    uint32_t mn = min(mnp & 0xffffu, mnp >> 16), mx = max(mxp & 0xffffu, mxp >> 16);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    __shared__ uint32_t s_mn[SINGLE_FAST_THREADS / 32], s_mx[SINGLE_FAST_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __shared__ unsigned s_ticket;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bmn = s_mn[0], bmx = s_mx[0];
+        for (int w = 1; w < SINGLE_FAST_THREADS / 32; w++) { bmn = min(bmn, s_mn[w]); bmx = max(bmx, s_mx[w]); }
+        atomicMin(&c->st.minP[1][blockIdx.x % STAT_BUCKETS][0], bmn);
+        atomicMax(&c->st.maxP[blockIdx.x % STAT_BUCKETS][0], bmx);
+        __threadfence();
+        s_ticket = atomicAdd(&c->ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) finish_single_fast(c, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// traceback
+// ------------------------------------------------------------------------------------------
 // Speculative segment walk.  Segment i covers bits [i*L, min((i+1)*L, nbits)).  Its end state is
 // guessed by walking `warm` extra stages back from state 0 (the true endstate for the last one).
 __global__ void k_chainback_seg(TraceArgs a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out,
@@ -273,26 +503,9 @@ __global__ void k_walk(TraceArgs a, long long dp, int delay, uint32_t endstate, 
 __global__ void k_walk_incremental(TraceArgs a, long long T, long long prev_T, int delay, uint32_t endstate, uint32_t *cache,
                                    unsigned long long *result, unsigned *steps_out)
 {
-    uint32_t st = endstate & STATEMASK;
-    int bit = -1;
-    unsigned steps = 0;
-    for (long long t = T - 1; t >= T - delay; t--) {
-        const long long row = ((t % a.len) + a.len) % a.len;
-        bit = (int)read_decision(a.ring, a.row_fmt, row, st);
-        st = ((uint32_t)bit << (K - 2)) | (st >> 1);
-        steps++;
-        const bool cached = t <= prev_T - 1 && t >= prev_T - delay && t > T - delay;
-        if (cached && cache[row] == st) {
-            // merged with the previous path: the state at time T - delay is the cached one
-            const long long r2 = (((T - delay) % a.len) + a.len) % a.len;
-            bit = (int)((cache[r2] >> (K - 2)) & 1u);
-            break;
-        }
-        cache[row] = st;
-    }
+    const int bit = incremental_walk(a.ring, a.row_fmt, a.len, T, prev_T, delay, endstate, cache, steps_out);
     result[0] = (unsigned long long)(long long)bit;
     result[1] = 0;
-    if (steps_out) atomicAdd(steps_out, steps);
 }
 
 // Batched streaming traceback: output i is what decodebit(delay, 0) returns right after stage
@@ -406,6 +619,7 @@ __global__ void k_import_ctl(Ctl *c, const uint16_t *m, const unsigned *mnmx, lo
     c->maxR = (long long)mnmx[1] - 32768;
     c->spread = (long long)mnmx[1] - (long long)mnmx[0];
     c->error = 0;
+    c->spec_first = 0;
     reset_stats(c);
 }
 
@@ -419,8 +633,18 @@ cudaError_t launch_init(uint16_t *m0, Ctl *c, uint32_t start_state, int bias, in
 }
 cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)
 {
-    if (sat) k_acs_single<true><<<NBFLY / 8 / 256, 256, 0, st>>>(a);
-    else     k_acs_single<false><<<NBFLY / 8 / 256, 256, 0, st>>>(a);
+    if (sat) { k_acs_single<true><<<NBFLY / 8 / 256, 256, 0, st>>>(a); return cudaGetLastError(); }
+    if (a.slow_form) { k_acs_single<false><<<NBFLY / 8 / 256, 256, 0, st>>>(a); return cudaGetLastError(); }
+    // two blocks of 512 threads per SM, all resident at once
+    static int sms_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = (dev >= 0 && dev < 64) ? sms_of[dev] : 0;
+    if (sms == 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (dev >= 0 && dev < 64) sms_of[dev] = sms;                 // (a benign race: every thread stores the same value)
+    }
+    k_acs_single_fast<<<2 * sms + (a.spec_walk ? 1 : 0), SINGLE_FAST_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,

@@ -2,7 +2,7 @@
 #pragma once
 #include "v224_common.cuh"
 
-namespace v224 {
+namespace V224_NS {
 
 struct PersistArgs {
     Ctl *ctl;
@@ -26,9 +26,21 @@ constexpr int MAX_CTX = 4;
 struct MultiArgs {
     int nctx;
     int npasses;             // per context
-    int grid_limit;          // 0: one CTA per resident slot (148 SMs x CTAs per SM); > 0: at most this many CTAs
+    int grid_limit;          // 0: one CTA per resident slot (148 SMs x CTAs per SM); > 0: at most this many CTAs; < 0: -grid_limit CTAs per SM
     PersistArgs ctx[MAX_CTX];
 };
+
+// Mapped pinned host memory the one-stage kernel reports into (per-bit ABI pattern, vdecode.c:145-152): the control-block
+// head the host mirrors, the result of the speculative decodebit walk, and -- written last, after a system-wide fence --
+// the sequence number of the launch.  The host polls `seq` instead of paying a copy and a stream synchronisation per call.
+struct Mailbox {
+    unsigned char ctl_head[256];         // the first CTL_HOST_BYTES of the control block after the stage
+    long long walk_bit;                  // decodebit(delay, endstate) at the new ring head (-2: no walk was asked for)
+    int declined;                        // the stage did not run (stale stage counter / saturation watch / error)
+    int pad;
+    volatile unsigned long long seq;
+};
+static_assert(CTL_HOST_BYTES <= 256, "mailbox control-block copy");
 
 struct SingleArgs {
     Ctl *ctl;
@@ -41,6 +53,16 @@ struct SingleArgs {
     long long expected_T;    // the control block's stage counter this launch was issued for (else it declines)
     int use_arg_syms;        // per-bit streaming: the two symbols travel as kernel arguments
     int sym0, sym1;
+    // per-bit streaming: report through the mailbox (NULL: no report), optionally with the decodebit walk the caller is about to ask for
+    Mailbox *mailbox;
+    unsigned long long seq;
+    int spec_walk, spec_delay;
+    uint32_t spec_end;
+    long long spec_prev_T;
+    uint32_t *walk_cache;
+    unsigned *walk_steps;
+    int all_canon;           // every row of the ring is in the canonical layout (the walk need not read the row tags)
+    int slow_form;           // test knob: the one-thread-per-8-butterflies scalar form of the stage instead of the packed one
 };
 
 struct TraceArgs {
@@ -70,4 +92,4 @@ cudaError_t launch_export_row(const TraceArgs &a, long long row, uint32_t *out, 
 cudaError_t launch_export_metrics(const uint16_t *m, const Ctl *c, int16_t *out, int *range_error, cudaStream_t st);
 cudaError_t launch_import_metrics(uint16_t *m, const int16_t *in, Ctl *c, unsigned *mnmx, long long renormals, long long T, cudaStream_t st);
 
-} // namespace v224
+} // namespace V224_NS

@@ -12,12 +12,17 @@
 #include <vector>
 #include <string>
 #include <thread>
+#include <atomic>
 #include <algorithm>
 #include "v224_kernels.h"
 #include "../../include/viterbi224.h"
 #include "../../include/viterbi224_b200.h"
 
 using namespace v224;
+
+// the fused pass compiled for 32-column tiles (v224_acs_persist.cu with -DV224_TILE_COLS_LOG2=5, namespace v224t32)
+extern "C" cudaError_t v224_t32_launch_persist(const void *multi_args, cudaStream_t st);
+extern "C" cudaError_t v224_t32_build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why);
 
 namespace {
 
@@ -110,7 +115,8 @@ struct Decoder {
     Ctl *ctl;
     Ctl *h_ctl;                 // pinned mirror, refreshed at the end of every update
     uint8_t *dsyms; size_t dsyms_cap;
-    void *tmaps;                            // NBUF tensor maps of the metric buffers (device memory)
+    void *tmaps;                            // NBUF tensor maps of the metric buffers (device memory), box = one 64-column tile
+    void *tmaps32;                          // the same with box = one 32-column tile (the fused pass of a decoder running alone)
     uint32_t *optab; size_t optab_cap;     // per-pass tables (operands + ring rows) of the running batch
     uint8_t *dout;  size_t dout_cap;       // chainback / stream output staging
     uint32_t *seg;  size_t seg_cap;        // chainback segment bookkeeping
@@ -125,13 +131,24 @@ struct Decoder {
     int cache_delay, cache_valid;
     uint32_t cache_end;
     unsigned *d_walk_steps;    // dependent loads spent in decodebit walks (test / tuning counter)
+    // per-bit streaming fast path: the one-stage kernel reports into mapped host memory and carries the decodebit walk
+    Mailbox *mb, *mb_dev;      // pinned mapped host memory / its device address
+    unsigned long long mb_seq; // sequence number of the last launch that reports through the mailbox
+    int mb_pending;            // that launch has not been waited for yet (h_ctl is stale until it has)
+    int spec_want, spec_delay; // the caller's decodebit pattern (set by decodebit): speculate on it in the next update(1)
+    uint32_t spec_end;
+    int spec_valid;            // the last stage carried the walk for (spec_delay, spec_end) at stage counter spec_T
+    long long spec_T, spec_bit;
+    int no_mailbox;            // option: always take the synchronous path
+    int slow_single;           // option: the scalar form of the one-stage kernel
+    int fused_rows;            // a fused pass has written rows into the ring since it was last cleared (their layout differs)
     // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
     struct Decoder *aux[2 * MAX_CTX - 1];   // [0, MAX_CTX-1): lockstep partners of this decoder; [MAX_CTX-1, ..): second lane set of the frame batches
     uint16_t *snap;
     int *d_segdiff;            // [2 * MAX_CTX]: min / max of the metric difference at each hand-over check
     cudaEvent_t ev0, ev1, kev0, kev1;
     // options
-    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache, grid_limit;
+    int force_single, force_sat, force_careful, per_pass_launch, chain_seg, chain_warm, no_walk_cache, grid_limit, tile32;
     // counters
     unsigned long long launches, acs_launches_timed, acs_passes_timed, chainback_redo;
     long long stages_total;                // trellis stages ever run on this ring (how many rows a recycled decoder has to clear)
@@ -140,13 +157,17 @@ struct Decoder {
     int time_kernels;
 };
 constexpr uint32_t MAGIC = 0x56323234u;   // "V224"
+constexpr int TILE32_DEFAULT = 1;         // which build of the fused pass a decoder running alone uses (option "tile32")
 constexpr int NAUX = 2 * MAX_CTX - 1;
+
+int mailbox_wait(struct Decoder *d);
 
 Decoder *as_dec(void *p)
 {
     Decoder *d = static_cast<Decoder *>(p);
     if (!d) return nullptr;
     if (d->magic != MAGIC) { set_err("not a viterbi224_b200 handle"); return nullptr; }
+    if (d->mb_pending && mailbox_wait(d)) return nullptr;      // an asynchronous per-bit stage is still in flight: h_ctl is stale until it reports
     return d;
 }
 
@@ -175,6 +196,82 @@ int sync_ctl(Decoder *d)
     return 0;
 }
 
+// Wait for the one-stage launch that reports through the mailbox (polling mapped host memory: no copy, no stream
+// synchronisation), then refresh the host's mirror of the control block from it.
+int mailbox_wait(Decoder *d)
+{
+    if (!d->mb_pending) return 0;
+    d->mb_pending = 0;
+    Mailbox *mb = d->mb;
+    bool arrived = false;
+    for (unsigned long long spins = 0; spins < 400ull * 1000 * 1000; spins++) {
+        if (mb->seq == d->mb_seq) { arrived = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xfffff) == 0xfffff && cudaStreamQuery(d->stream) != cudaErrorNotReady) {
+            // the stream is idle (or broken): the report is there now or never
+            arrived = mb->seq == d->mb_seq;
+            break;
+        }
+    }
+    if (!arrived) {
+        const cudaError_t e = cudaStreamSynchronize(d->stream);
+        if (mb->seq != d->mb_seq) { set_err("per-bit stage did not report (%s)", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (mb->declined) { set_err("per-bit stage declined to run (stage %lld)", d->h_ctl->T); return -1; }
+    memcpy(d->h_ctl, mb->ctl_head, CTL_HOST_BYTES);
+    d->spec_bit = mb->walk_bit;
+    if (d->h_ctl->error) { set_err("device control block reports invariant violation %d", d->h_ctl->error); return -1; }
+    return 0;
+}
+
+// update_viterbi224_blk(p, syms, 1) of the per-bit streaming pattern (vdecode.c:145): ONE asynchronous launch.  The host
+// knows from its (fresh) mirror of the control block whether the stage can renormalise or needs the saturating variant; if
+// neither, the call returns 0 -- the reference's return value -- without waiting, and the next call picks the report up.
+// The launch also carries the decodebit walk the caller asked for after the previous stage (vdecode.c:152).
+// Returns -2 when the fast path does not apply (the caller then takes the synchronous path).
+int update_one_fast(Decoder *d, int s0, int s1)
+{
+    if (d->no_mailbox || d->force_sat || d->time_kernels || !d->mb) return -2;
+    const Ctl *h = d->h_ctl;
+    if (h->error || h->maxR + 510 > 32767 || h->spread > MAX_FAST_SPREAD) return -2;      // what k_acs_single<false> checks itself
+    const long long T = h->T;
+    SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, nullptr, d->len, 0, T, 1, s0, s1};
+    a.mailbox = d->mb_dev;
+    a.seq = ++d->mb_seq;
+    a.slow_form = d->slow_single;
+    d->spec_valid = 0;
+    if (d->spec_want && d->spec_delay < d->len && !d->no_walk_cache) {
+        if (!d->walk_cache) {
+            CU(cudaMalloc(&d->walk_cache, (size_t)d->len * sizeof(uint32_t)));
+            CU(cudaMalloc(&d->d_walk_steps, sizeof(unsigned)));
+            CU(cudaMemsetAsync(d->d_walk_steps, 0, sizeof(unsigned), d->stream));
+        }
+        const long long Tn = T + 1;
+        const bool inc = d->cache_valid && d->cache_delay == d->spec_delay && d->cache_end == d->spec_end && Tn > d->cache_T && Tn - d->cache_T < d->spec_delay;
+        a.spec_walk = 1;
+        a.spec_delay = d->spec_delay;
+        a.spec_end = d->spec_end;
+        a.spec_prev_T = inc ? d->cache_T : Tn - 4ll * d->len - 4ll * d->spec_delay;
+        a.walk_cache = d->walk_cache;
+        a.walk_steps = d->d_walk_steps;
+        a.all_canon = d->fused_rows ? 0 : 1;
+        d->cache_valid = 1; d->cache_T = Tn; d->cache_delay = d->spec_delay; d->cache_end = d->spec_end;
+        d->spec_valid = 1;
+        d->spec_T = Tn;
+    }
+    CU(launch_single(a, false, d->stream));
+    d->launches++;
+    d->stages_total++;
+    d->mb_pending = 1;
+    const int ren0 = h->renorm_count;
+    if (h->R0 + 510 < RENORM_TRIGGER) return 0;        // state 0 cannot reach the trigger in this stage (viterbi224_sse2.c:351)
+    if (mailbox_wait(d)) return -1;
+    return d->h_ctl->renorm_count - ren0;
+}
+
 // ---- recycled decoders: decode.c:216-229 creates and deletes a 1024-row decoder PER FRAME.  A create / delete pair
 // costs ~6 ms of allocations (pinned host memory, streams, events, tensor maps); a recycled decoder only clears the ring
 // rows it ever wrote and re-runs init.  At most DEC_POOL_MAX decoders wait here, none with auxiliary decoders attached. ----
@@ -191,11 +288,12 @@ void destroy(Decoder *d)
     if (d->ring) pool_put(d->dev, d->ring_bytes, d->ring);
     for (int i = 0; i < NBUF; i++) cudaFree(d->metrics[i]);
     cudaFree(d->row_fmt); cudaFree(d->ctl);
-    cudaFree(d->optab); cudaFree(d->tmaps);
+    cudaFree(d->optab); cudaFree(d->tmaps); cudaFree(d->tmaps32);
     cudaFree(d->dsyms); cudaFree(d->dout); cudaFree(d->seg); cudaFree(d->d_redo); cudaFree(d->d_key);
     cudaFree(d->d_mnmx); cudaFree(d->d_result); cudaFree(d->d_flag); cudaFree(d->snap); cudaFree(d->d_segdiff); cudaFree(d->walk_cache); cudaFree(d->d_walk_steps);
     if (d->h_ctl) cudaFreeHost(d->h_ctl);
     if (d->h_result) cudaFreeHost(d->h_result);
+    if (d->mb) cudaFreeHost(d->mb);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->kev0) cudaEventDestroy(d->kev0);
@@ -221,6 +319,7 @@ int do_init(Decoder *d, int bias, int start_state)
     if (bind(d)) return -1;
     const uint32_t ss = start_state < 0 ? 0u : ((uint32_t)start_state & STATEMASK);
     d->cache_valid = 0;
+    d->spec_valid = 0;
     CU(launch_init(d->metrics[0], d->ctl, ss, bias, start_state < 0 ? -1 : 0, d->stream));
     d->launches++;
     if (sync_ctl(d)) return -1;
@@ -235,7 +334,11 @@ int recycle(Decoder *d)
 {
     if (bind(d)) return -1;
     d->magic = MAGIC;
-    d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = d->grid_limit = 0;
+    d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = d->grid_limit = d->no_mailbox = 0;
+    d->spec_want = d->spec_valid = 0;
+    d->slow_single = 0;
+    d->fused_rows = 0;                       // every row it ever wrote is cleared below, tags included
+    d->tile32 = TILE32_DEFAULT;
     d->chain_seg = 128;
     d->chain_warm = 256;
     d->launches = d->acs_launches_timed = d->acs_passes_timed = d->chainback_redo = 0;
@@ -263,6 +366,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
 {
     if (nbits <= 0) return 0;
     d->stages_total += nbits;
+    d->spec_valid = 0;
     const long long T_start = d->h_ctl->T;
     const int ren_start = d->h_ctl->renorm_count;
     constexpr int BATCH_STAGES = 8192;
@@ -277,6 +381,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         if (fuse && end - p >= FK) {
             // one persistent launch runs all full passes of this batch as a dataflow ("per_pass_launch": one launch per pass)
             const int total = (end - p) / FK;
+            d->fused_rows = 1;
             // two passes of one persistent launch may be in flight at once: with fewer than 2 * FK ring rows they would
             // write the same row, so such rings get one launch per pass
             const int per_launch = (d->per_pass_launch || d->len < 2 * FK) ? 1 : total;
@@ -286,10 +391,16 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
                 MultiArgs m;
                 m.nctx = 1;
                 m.npasses = npasses;
-                m.grid_limit = d->grid_limit;
-                m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->tmaps, d->optab, d->len, p,
-                                       (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
-                CU(launch_persist(m, d->stream));
+                // a decoder alone is latency bound (pass n+1 needs all of pass n).  64-column tiles: one CTA per SM finishes a tile
+                // sooner than three sharing the SM, and the pass with it (13.6 instead of 15.3 us); 32-column tiles (the default
+                // for a lone decoder): half the tile latency and finer dependencies, 12.9 us (profiles/r02_probe_*.txt)
+                m.grid_limit = d->grid_limit > 0 ? d->grid_limit : -1;
+                // a decoder alone runs the 32-column-tile build of the pass ("tile32" = 0: the 64-column one)
+                const bool t32 = d->tile32 != 0;
+                m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, t32 ? d->tmaps32 : d->tmaps, d->optab,
+                                       d->len, p, (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
+                if (t32) { m.grid_limit = d->grid_limit > 0 ? d->grid_limit : -3; CU(v224_t32_launch_persist(&m, d->stream)); }   // 3 of 5 possible CTAs per SM: measured optimum
+                else CU(launch_persist(m, d->stream));
                 p += npasses * FK;
                 n += 3;
             }
@@ -298,6 +409,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
         while (p < end) {
             SingleArgs a{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, d->len, p, T_start + p,
                          arg_s0 >= 0, arg_s0, arg_s1};
+            a.slow_form = d->slow_single;
             CU(launch_single(a, d->force_sat != 0, d->stream));
             p += 1;
             n++;
@@ -344,7 +456,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
     const int fused_total = nbits / FK * FK;
     int pos = 0;
     bool lockstep = true;
-    for (int s = 0; s < nctx; s++) ds[s]->stages_total += nbits;
+    for (int s = 0; s < nctx; s++) { ds[s]->stages_total += nbits; ds[s]->spec_valid = 0; }
     for (int s = 0; s < nctx; s++) if (ds[s]->force_single || ds[s]->force_sat || ds[s]->len < 2 * FK) lockstep = false;
     while (lockstep && pos < fused_total) {
         const int end = std::min(fused_total, pos + BATCH_STAGES);
@@ -352,9 +464,10 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         MultiArgs m;
         m.nctx = nctx;
         m.npasses = npasses;
-        m.grid_limit = d0->grid_limit;
+        m.grid_limit = d0->grid_limit > 0 ? d0->grid_limit : (nctx == 1 ? -1 : 0);
         for (int s = 0; s < nctx; s++) {
             Decoder *d = ds[s];
+            d->fused_rows = 1;
             if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
             m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->tmaps, d->optab, d->len,
                                    pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
@@ -462,7 +575,7 @@ void swap_bodies(Decoder *d, Decoder *o)
     o->ev0 = to.ev0; o->ev1 = to.ev1; o->kev0 = to.kev0; o->kev1 = to.kev1;
     d->force_single = td.force_single; d->force_sat = td.force_sat; d->force_careful = td.force_careful;
     d->per_pass_launch = td.per_pass_launch; d->chain_seg = td.chain_seg; d->chain_warm = td.chain_warm; d->no_walk_cache = td.no_walk_cache;
-    d->grid_limit = td.grid_limit;
+    d->grid_limit = td.grid_limit; d->tile32 = td.tile32;
     d->time_kernels = td.time_kernels; d->acs_ms = td.acs_ms; d->acs_launches_timed = td.acs_launches_timed;
     d->acs_passes_timed = td.acs_passes_timed; d->launches = td.launches;
     o->time_kernels = to.time_kernels; o->acs_ms = to.acs_ms; o->acs_launches_timed = to.acs_launches_timed;
@@ -876,14 +989,16 @@ void *create_viterbi224(int len)
     d->len = len;
     d->chain_seg = 128;
     d->chain_warm = 256;
+    d->tile32 = TILE32_DEFAULT;
     d->ring_bytes = (size_t)len * ROWBYTES;
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < NBUF; i++) ok = ok && cudaMalloc(&d->metrics[i], METRICBYTES) == cudaSuccess;
-    ok = ok && cudaMalloc(&d->tmaps, NBUF * TMAP_BYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->tmaps, NBUF * TMAP_BYTES) == cudaSuccess && cudaMalloc(&d->tmaps32, NBUF * TMAP_BYTES) == cudaSuccess;
     if (ok) {
         const char *why = nullptr;
-        if (build_metric_tensor_maps(d->metrics, d->tmaps, d->stream, &why) != cudaSuccess) {
+        if (build_metric_tensor_maps(d->metrics, d->tmaps, d->stream, &why) != cudaSuccess ||
+            v224_t32_build_metric_tensor_maps(d->metrics, d->tmaps32, d->stream, &why) != cudaSuccess) {
             set_err("create_viterbi224(%d): tensor maps: %s", len, why ? why : cudaGetErrorString(cudaGetLastError()));
             destroy(d);
             return nullptr;
@@ -898,6 +1013,9 @@ void *create_viterbi224(int len)
     ok = ok && cudaMalloc(&d->d_flag, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost(&d->h_ctl, sizeof(Ctl)) == cudaSuccess;
     ok = ok && cudaMallocHost(&d->h_result, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&d->mb, sizeof(Mailbox), cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer(reinterpret_cast<void **>(&d->mb_dev), d->mb, 0) == cudaSuccess;
+    if (ok) memset(d->mb, 0, sizeof(Mailbox));
     ok = ok && cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
     ok = ok && cudaEventCreate(&d->kev0) == cudaSuccess && cudaEventCreate(&d->kev1) == cudaSuccess;
     if (ok) {
@@ -932,8 +1050,13 @@ int update_viterbi224_blk(void *p, const unsigned char *syms, int nbits)
     if (!d) return -1;
     if (nbits <= 0) return 0;
     if (bind(d)) return -1;
-    if (nbits == 1)      // vdecode.c:145 -- the two symbols ride in the kernel arguments
+    if (nbits == 1) {    // vdecode.c:145 -- the two symbols ride in the kernel arguments
+        const int r = update_one_fast(d, syms[0], syms[1]);
+        if (r != -2) return r;
+        d->spec_valid = 0;
         return update_core(d, nullptr, 1, syms[0], syms[1]);
+    }
+    d->spec_valid = 0;
     if (grow((void **)&d->dsyms, &d->dsyms_cap, 2 * (size_t)nbits)) return -1;
     CU(cudaMemcpyAsync(d->dsyms, syms, 2 * (size_t)nbits, cudaMemcpyHostToDevice, d->stream));
     return update_core(d, d->dsyms, nbits);
@@ -1000,7 +1123,12 @@ int decodebit_viterbi224(void *p, int delay, int endstate)
     if (!d) return -1;
     if (delay <= 0) return -1;
     if (endstate >= 0 && delay < d->len && !d->no_walk_cache) {
-        if (walk_incremental(d, delay, (uint32_t)endstate & STATEMASK)) return -1;
+        const uint32_t es = (uint32_t)endstate & STATEMASK;
+        // the stage that just ran carried exactly this walk (asked for after the previous stage): the answer is in the mailbox
+        if (d->spec_valid && d->spec_T == d->h_ctl->T && d->spec_delay == delay && d->spec_end == es && d->spec_bit >= -1)
+            return (int)d->spec_bit;
+        d->spec_want = 1; d->spec_delay = delay; d->spec_end = es;      // the next update(1) brings the walk along
+        if (walk_incremental(d, delay, es)) return -1;
     } else if (walk(d, delay, endstate)) return -1;
     return (int)(long long)d->h_result[0];
 }
@@ -1414,6 +1542,7 @@ int v224x_set_state(void *p, const int16_t *host_metrics, long long renormals, l
     Decoder *d = as_dec(p);
     if (!d || bind(d)) return -1;
     d->cache_valid = 0;
+    d->spec_valid = 0;
     d->ring_dirty_all = 1;
     int16_t *tmp = nullptr;
     CU(cudaMalloc(&tmp, METRICBYTES));
@@ -1456,6 +1585,9 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "per_pass_launch")) d->per_pass_launch = (int)value;
     else if (!strcmp(key, "no_walk_cache")) d->no_walk_cache = (int)value;
     else if (!strcmp(key, "grid_limit")) d->grid_limit = (int)std::max(0ll, value);
+    else if (!strcmp(key, "no_mailbox")) d->no_mailbox = (int)value;
+    else if (!strcmp(key, "tile32")) d->tile32 = (int)value;
+    else if (!strcmp(key, "slow_single")) d->slow_single = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

@@ -9,7 +9,7 @@
 #include <vector>
 #include "../../isee3-decoder_b200/csrc/v224_fused_core.cuh"
 
-using namespace v224;
+using namespace V224_NS;
 
 template <int T>
 static void emu_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *optab, uint32_t *rows, uint32_t chunk,
@@ -24,15 +24,13 @@ static void emu_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *op
     if (mn < minP[T]) minP[T] = mn;
 }
 
-// the kernel's shared-memory exchange index (k_acs_persist: xchg_index)
-static uint32_t xchg_index(uint32_t m, uint32_t g)
-{
-    return NQ == 2 ? m * FUSED_COLGROUPS + (g ^ ((m >> 1) & 8u)) : m * FUSED_COLGROUPS + g;
-}
+// (the shared-memory exchange index xchg_index() is the kernel's own, from v224_common.cuh)
 
 extern "C" {
 
 int emu_nq(void) { return NQ; }
+int emu_tile_cols(void) { return FUSED_TILE_COLS; }
+int emu_rowfmt_base(void) { return ROWFMT_FUSED_BASE; }
 
 // One fused pass: oldP/newP 2^23 uint16, rows = 8 decision rows in fused layout, syms = 16 bytes.
 // stats: s0[1..8], minP[1..8], maxP_end written to out_stats[0..8], [9..17], [18].

@@ -115,17 +115,21 @@ def test_channel_restatement_equals_reference_simulate(built):
     assert abs(mean1 - 152) < 1.5 and abs(mean0 - 104) < 1.5
 
 
-def _emu():
-    so = os.path.join(os.path.dirname(__file__), "emu", "_build", "libfused_emu.so")
+def _emu(name="libfused_emu.so"):
+    so = os.path.join(os.path.dirname(__file__), "emu", "_build", name)
     return ctypes.CDLL(so)
 
 
-@pytest.mark.parametrize("seed,warm", [(7, 40), (8, 3), (9, 25)])
-def test_fused_pass_index_algebra_against_oracle(built, seed, warm):
+@pytest.mark.parametrize("lib,seed,warm", [("libfused_emu.so", 7, 40), ("libfused_emu.so", 8, 3), ("libfused_emu.so", 9, 25),
+                                           ("libfused_emu_t32.so", 7, 40), ("libfused_emu_t32.so", 10, 5)])
+def test_fused_pass_index_algebra_against_oracle(built, lib, seed, warm):
     """Host emulation of the fused kernel's arithmetic core (same header, same per-thread data movement and thread
-    maps of both register rounds): metrics, all eight decision rows (through fused_bit_address) and state-0
-    tracking equal the oracle."""
-    e = _emu()
+    maps of both register rounds), for both tile widths the library builds (64 columns: lockstep decoders, 32 columns: a
+    decoder running alone): metrics, all eight decision rows (through fused_bit_address) and state-0 tracking equal the
+    oracle."""
+    e = _emu(lib)
+    assert e.emu_tile_cols() == (32 if "t32" in lib else 64)
+    fmt_base = e.emu_rowfmt_base()
     rng = np.random.default_rng(seed)
     syms = rng.integers(40, 216, 2 * (warm + 8), dtype=np.uint8)
     with pyoracle.Oracle(warm + 8) as o:
@@ -146,7 +150,7 @@ def test_fused_pass_index_algebra_against_oracle(built, seed, warm):
             assert int(stats[t]) + sub - 32768 == int(mt[0]), f"state-0 metric after stage {t}"
             assert int(stats[9 + t]) + sub - 32768 == int(mt.min()), f"global min after stage {t}"
             canon = np.zeros(1 << 18, np.uint32)
-            e.emu_canon_row(t, rows[t - 1].ctypes.data_as(vp), canon.ctypes.data_as(vp))
+            e.emu_canon_row(fmt_base + t, rows[t - 1].ctypes.data_as(vp), canon.ctypes.data_as(vp))
             assert np.array_equal(canon, o.get_row(warm + t - 1)), f"decision row of stage {t}"
         m1 = o.get_metrics()
     assert np.array_equal(newP.astype(np.int64) + sub - 32768, m1.astype(np.int64))
