@@ -5,16 +5,21 @@
 //   k_build_passtab  per-pass operand tables + ring rows
 //   k_persist_begin  launch prologue on the control block
 //
-// CTA = COMPUTE_WARPS compute warps + 1 protocol warp (warp specialisation).  The protocol warp runs the dataflow
-// one tile ahead of the compute warps: it claims the next (pass, decoder, tile) item, fetches the pass table, polls
-// the pass parameters and the previous pass's completion counters (all L2 round trips), and hands the tile over
-// through a shared-memory mbarrier; when the compute warps have issued a tile's stores it publishes the tile
-// (release) and, for the last tile of a pass, runs the resolver.  The compute warps therefore never wait for an
-// L2 round trip of the protocol, only for data.
+// CTA = FUSED_THREADS / 32 compute warps + 2 protocol warps (warp specialisation: producer and retirer), 64 registers per
+// thread.  The producer runs the dataflow one tile ahead of the compute warps: it claims the next (pass, decoder, tile)
+// item, polls the pass parameters and the previous pass's completion counters (L2 round trips), issues the tile's
+// tensor copy and the pass table's bulk copy (TMA) and hands the tile over through a shared-memory mbarrier.  The
+// retirer waits until the compute warps have issued a tile's stores, publishes the tile (release) and, for the last
+// tile of a pass, runs the resolver.  The compute warps therefore never wait for an L2 round trip of the protocol,
+// only for data.
+//
+// Built twice (isee3-decoder_b200/build.py): tiles of 64 columns -- 256 compute threads, 3 CTAs per SM, the shape of
+// the lockstep multi-decoder launches -- and tiles of 32 columns (-DV224_TILE_COLS_LOG2=5, namespace v224t32) -- 128
+// compute threads, up to 5 CTAs per SM, for a decoder running alone.
 //
 // This file is compiled with -Xptxas -O1: at the default level ptxas hoists the decision-bit gather of a whole stage
-// behind the butterflies and spills (≈500 bytes per thread at 64 registers); in source order the tile body needs
-// no spill at all (see csrc/ptxas.log, profiles/).
+// behind the butterflies and spills (~500 bytes per thread at 64 registers); in source order the tile body spills
+// one register (4 bytes stored / 8 loaded per thread in the 64-column build, 12 / 24 in the 32-column build: csrc/ptxas.log).
 #include "v224_common.cuh"
 #include "v224_fused_core.cuh"
 #include "v224_kernels.h"

@@ -58,8 +58,9 @@ static_assert(FUSED_COLS_LOG2 == 6 || FUSED_COLS_LOG2 == 5, "tile width");
 constexpr int FUSED_TILE_COLS = 1 << FUSED_COLS_LOG2;  // columns (j) per tile
 constexpr int FUSED_COLGROUPS = FUSED_TILE_COLS / COLW; // column groups (one per thread column) per tile: 16 / 8
 constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column groups: 256 / 128
-// CTA = FUSED_THREADS compute threads + one protocol warp (v224_acs_persist.cu).  3 CTAs of 288 threads per SM at 72
-// registers; the round-1 -> round-2 exchange buffer is double-buffered when shared memory allows (3 x 67 KiB).
+// CTA = FUSED_THREADS compute threads + two protocol warps (v224_acs_persist.cu) at 64 registers: 3 CTAs of 320 threads per
+// SM with 64-column tiles, up to 5 CTAs of 192 threads with 32-column tiles; the round-1 -> round-2 exchange buffer is
+// double-buffered (it doubles as the landing zone of the next tile's tensor copy): 3 x 67 KiB / 5 x 35 KiB of shared memory.
 #ifndef V224_CTAS_PER_SM
 #define V224_CTAS_PER_SM (V224_TILE_COLS_LOG2 == 6 ? 3 : 5)
 #endif
@@ -68,7 +69,7 @@ constexpr int FUSED_CTAS_PER_SM = V224_CTAS_PER_SM;
 #define V224_XCHG_BUFS ((V224_CTAS_PER_SM <= 3 || V224_TILE_COLS_LOG2 == 5) ? 2 : 1)
 #endif
 constexpr int XCHG_BUFS = V224_XCHG_BUFS;
-// The protocol warp prefetches a tile's input into its exchange buffer with bulk asynchronous copies (TMA engine)
+// The producer warp prefetches a tile's input into its exchange buffer with one tensor copy (TMA engine)
 // while the compute warps still work on the previous tile; needs the double buffer.
 #ifndef V224_BULK_LOAD
 #define V224_BULK_LOAD (V224_XCHG_BUFS == 2)

@@ -60,7 +60,11 @@ public:
     // cmp_out is not NULL, 2 bytes at cmp_out (the hard-sliced history symbols vdecode compares the re-encoded pair
     // with, vdecode.c:176-177).  Both need room for n/2 + 1 pairs.  Every phase flip appends the index of the next pair
     // (counted since construction) to *flips, if given.  Returns the number of pairs produced by this call.
-    size_t feed(const unsigned char *in, size_t n, unsigned char *syms_out, unsigned char *cmp_out, std::vector<unsigned long long> *flips)
+    // pre (optional): pre[i] = correlation of in[i-33 .. i] taken over the input as it stands (correlate_block(), which
+    // callers may run on slices of the buffer in parallel); it is used wherever the 34 newest history symbols ARE the 34
+    // newest input symbols, i.e. everywhere except right behind the start of the stream and behind a dropped symbol.
+    size_t feed(const unsigned char *in, size_t n, unsigned char *syms_out, unsigned char *cmp_out, std::vector<unsigned long long> *flips,
+                const int16_t *pre = nullptr)
     {
         size_t npairs = 0;
         while (n) {
@@ -69,7 +73,8 @@ public:
                 // no decision can fall inside the run: it ends at the odd-slot symbol that completes the frame count
                 const size_t odd_needed = (size_t)(FRAME_SYMBOLS - frame_count_);
                 count = std::min(n, (slot_ & 1) ? 2 * odd_needed - 1 : 2 * odd_needed);
-                correlate_run(in, count);
+                correlate_run(in, count, pre);
+                if (pre) pre += count;
             }
             if (cmp_out) npairs += emit_run_with_history(in, count, syms_out + 2 * npairs, cmp_out + 2 * npairs, flips, npairs);
             else         npairs += emit_run(in, count, syms_out + 2 * npairs, flips, npairs);
@@ -81,27 +86,54 @@ public:
         return npairs;
     }
 
+    // pre[i] for i in [from, to): the correlation of in[i-33 .. i] (positions before the buffer count as erasures; feed()
+    // never uses those).  Independent of all state: callers may run it on slices of a buffer in parallel.
+    static void correlate_block(const unsigned char *in, size_t from, size_t to, int16_t *pre)
+    {
+        int taps[NTAPS];
+        sync_taps(taps);
+        constexpr size_t CH = 1 << 15;
+        std::vector<int16_t> lin(CH + NTAPS - 1 + 16);
+        for (size_t a = from; a < to; a += CH) {
+            const size_t b = std::min(to, a + CH);
+            for (size_t k = 0; k < NTAPS - 1; k++) lin[k] = a + k >= NTAPS - 1 ? (int16_t)((int)in[a + k - (NTAPS - 1)] - 128) : (int16_t)0;
+            widen(in + a, b - a, lin.data() + NTAPS - 1);
+            correlate(lin.data(), b - a, taps, pre + a);
+        }
+    }
+
     int phase() const { return slot_ & 1; }
     unsigned long long pairs_total() const { return pairs_total_; }
 
 private:
     // sums[i] = correlation of the 34 newest symbols after in[i] arrived (vdecode.c:111-117); peaks per slot parity
-    void correlate_run(const unsigned char *in, size_t count)
+    void correlate_run(const unsigned char *in, size_t count, const int16_t *pre)
     {
-        lin_.resize(count + NTAPS - 1 + 16);
-        acc_.resize(count + 16);
+        // the first `own` symbols of the run still see history that is not plain input (preset ring, a dropped symbol)
+        const size_t own = pre ? std::min(count, stale_) : count;
+        lin_.resize(own + NTAPS - 1 + 16);
         std::memcpy(lin_.data(), tail_, (NTAPS - 1) * sizeof(int16_t));
-        widen(in, count, lin_.data() + NTAPS - 1);
-        correlate(lin_.data(), count, taps_, acc_.data());
+        widen(in, own, lin_.data() + NTAPS - 1);
+        acc_.resize(own + 16);
+        correlate(lin_.data(), own, taps_, acc_.data());
+        stale_ -= std::min(stale_, count);
+        int pe = -1000000, po = -1000000;              // peaks on in[even i] / in[odd i]
+        peaks(acc_.data(), 0, own, pe, po);
+        if (pre) peaks(pre, own, count, pe, po);
         // in[i] lands on slot slot_ + i: even slots feed the out-of-phase peak, odd slots the in-phase one
-        int pe = -1000000, po = -1000000;
-        const int16_t *a = acc_.data();
-        size_t i = 0;
-        for (; i + 1 < count; i += 2) { pe = std::max(pe, (int)a[i]); po = std::max(po, (int)a[i + 1]); }
-        if (i < count) pe = std::max(pe, (int)a[i]);
         if (slot_ & 1) std::swap(pe, po);              // in[0] sits on an odd slot
         peak_out_ = std::max(peak_out_, pe);
         peak_in_ = std::max(peak_in_, po);
+    }
+    static void peaks(const int16_t *a, size_t from, size_t to, int &pe, int &po)
+    {
+        int16_t me = -32768, mo = -32768;
+        size_t i = from;
+        if (i < to && (i & 1)) { mo = std::max(mo, a[i]); i++; }
+        for (; i + 1 < to; i += 2) { me = std::max(me, a[i]); mo = std::max(mo, a[i + 1]); }
+        if (i < to) me = std::max(me, a[i]);
+        if (me > -32768) pe = std::max(pe, (int)me);
+        if (mo > -32768) po = std::max(po, (int)mo);
     }
     static void widen(const unsigned char *in, size_t count, int16_t *out)
     {
@@ -191,13 +223,15 @@ private:
     void carry_tail(const unsigned char *in, size_t count)
     {
         const size_t kept = count - (dropped_last_ ? 1 : 0);
+        if (dropped_last_) stale_ = NTAPS - 1;         // the window of the next 33 symbols skips the dropped one
         dropped_last_ = false;
-        const int16_t *src = lin_.data();              // previous tail followed by this run
-        const size_t total = NTAPS - 1 + kept;
-        int16_t t[NTAPS - 1];
-        for (int k = 0; k < NTAPS - 1; k++) t[k] = src[total - (NTAPS - 1) + k];
-        std::memcpy(tail_, t, sizeof t);
-        (void)in;
+        constexpr size_t H = NTAPS - 1;
+        if (kept >= H) {
+            for (size_t k = 0; k < H; k++) tail_[k] = (int16_t)((int)in[kept - H + k] - 128);
+        } else {
+            std::memmove(tail_, tail_ + kept, (H - kept) * sizeof(int16_t));
+            for (size_t k = 0; k < kept; k++) tail_[H - kept + k] = (int16_t)((int)in[k] - 128);
+        }
     }
 
     unsigned char ring_[RING];
@@ -209,6 +243,7 @@ private:
     unsigned char even_sym_ = 0;       // the last symbol that landed on an even slot (first half of the next pair)
     int frame_count_ = 0, peak_in_ = -1000000, peak_out_ = -1000000;
     bool dropped_last_ = false;
+    size_t stale_ = NTAPS - 1;         // upcoming symbols whose 34-symbol window still holds non-input history
     unsigned long long pairs_total_ = 0;
     std::vector<int16_t> lin_, acc_;
 };
