@@ -490,7 +490,7 @@ def main():
     my_lead, my_nout = me.out_first - me.stage_first, me.out_last - me.out_first
     longest = max(s.out_last - s.out_first for s in segs)
     dsyms = torch.empty(2 * (me.out_last - me.stage_first), dtype=torch.uint8, device=dev)
-    dbits = torch.zeros(longest, dtype=torch.uint8, device=dev)
+    dbits = torch.empty(longest, dtype=torch.uint8, device=dev)
     if on_gpu:
         tx_range, sym_range = gpu_stream_range(torch, dev, me.stage_first, me.out_last)
         dsyms.copy_(sym_range)
@@ -501,7 +501,7 @@ def main():
     else:
         dec.h2d(dsyms.data_ptr(), np.ctypeslib.as_array(ctypes.cast(hp_pairs, ctypes.POINTER(ctypes.c_uint8)), (2 * cap,))[2 * me.stage_first: 2 * me.out_last])
     torch.cuda.synchronize()
-    gathered = [torch.zeros(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gathered = [torch.empty(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     hp_out = lib.v224x_host_alloc_pinned(npairs) if rank == 0 else None
     out_host = np.ctypeslib.as_array(ctypes.cast(hp_out, ctypes.POINTER(ctypes.c_uint8)), (npairs,)) if rank == 0 else None
     redo_bufs = []
@@ -517,7 +517,7 @@ def main():
             torch.cuda.synchronize()
         else:
             dec.h2d(s.data_ptr(), np.ctypeslib.as_array(ctypes.cast(hp_pairs, ctypes.POINTER(ctypes.c_uint8)), (2 * cap,))[2 * a: 2 * b])
-        o = torch.zeros(b - a, dtype=torch.uint8, device=dev)
+        o = torch.empty(b - a, dtype=torch.uint8, device=dev)
         redo_bufs.append((s, o))
         return s, o
 

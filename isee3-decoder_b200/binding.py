@@ -45,7 +45,8 @@ class SegReport(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libviterbi224_b200.so")
+    # V224_LIB: an A/B build of the library (tools/build_variants.sh) instead of the in-tree one -- measurement runs only
+    return os.environ.get("V224_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libviterbi224_b200.so")
 
 
 _lib = None

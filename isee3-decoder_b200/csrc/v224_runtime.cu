@@ -339,8 +339,8 @@ int recycle(Decoder *d)
     d->slow_single = 0;
     d->fused_rows = 0;                       // every row it ever wrote is cleared below, tags included
     d->tile32 = TILE32_DEFAULT;
-    d->chain_seg = 128;
-    d->chain_warm = 256;
+    d->chain_seg = 64;
+    d->chain_warm = 192;
     d->launches = d->acs_launches_timed = d->acs_passes_timed = d->chainback_redo = 0;
     d->acs_ms = 0;
     d->time_kernels = 0;
@@ -987,8 +987,8 @@ void *create_viterbi224(int len)
     d->magic = MAGIC;
     d->dev = dev;
     d->len = len;
-    d->chain_seg = 128;
-    d->chain_warm = 256;
+    d->chain_seg = 64;
+    d->chain_warm = 192;
     d->tile32 = TILE32_DEFAULT;
     d->ring_bytes = (size_t)len * ROWBYTES;
     bool ok = true;
