@@ -11,8 +11,14 @@ LIB = os.path.join(HERE, "libviterbi224_b200.so")
 # decision-bit gather behind a whole stage of butterflies and spills; in source order the tile body needs no spill.
 # The fused pass is built twice: 64-column tiles (lockstep decoders) and 32-column tiles (a decoder running alone).
 SOURCES = [("v224_acs_persist.cu", ["-Xptxas", "-O1"], "v224_acs_persist.o"),
-           ("v224_acs_persist.cu", ["-Xptxas", "-O1", "-DV224_TILE_COLS_LOG2=5", "-DV224_NS=v224t32"], "v224_acs_persist_t32.o"),
+           ("v224_acs_persist.cu", ["-Xptxas", "-O1", "-DV224_TILE_COLS_LOG2=5", "-DV224_NS=v224t32", "-DV224_BRIDGE=v224_t32"], "v224_acs_persist_t32.o"),
+
            ("v224_kernels.cu", [], "v224_kernels.o"), ("v224_runtime.cu", [], "v224_runtime.o")]
+# A/B only (build.py --out ... -DV224_WITH_Q1): 32-column tiles with ONE packed register per row and thread (256 threads on half a
+# tile's work).  Correct (emulated on the CPU tier, all golden variants on the GPU) but slower than the two-register build for a lone
+# decoder (13.9 against 12.9 us per pass) and in lockstep (10.5 against 9.1): profiles/r02_probe_one_register_build.txt.
+Q1_SOURCE = ("v224_acs_persist.cu", ["-Xptxas", "-O1", "-DV224_TILE_COLS_LOG2=5", "-DV224_NQ=1", "-DV224_NS=v224t32q1", "-DV224_BRIDGE=v224_t32q1"],
+             "v224_acs_persist_t32q1.o")
 HOST_SOURCES = ["v224_pairing.cpp"]           # plain C++ (g++ -O3): host-side entries of the library, no CUDA
 HEADERS = ["v224_common.cuh", "v224_fused_core.cuh", "v224_kernels.h", "v224_pairing.cpp", os.path.join("..", "host", "pairing.h"),
            os.path.join("..", "..", "include", "viterbi224.h"), os.path.join("..", "..", "include", "viterbi224_b200.h")]
@@ -65,7 +71,7 @@ def build_library(force=False, verbose=False, out=None, extra_flags=()):
     nvcc = nvcc_path()
     objs = []
     log = []
-    for s, flags, oname in SOURCES:
+    for s, flags, oname in SOURCES + ([Q1_SOURCE] if "-DV224_WITH_Q1" in extra_flags else []):
         o = (out + "." if variant else os.path.join(CSRC, "")) + oname
         cmd = [nvcc, *NVCC_FLAGS, *flags, *extra_flags, "-c", "-o", o, os.path.join(CSRC, s)]
         r = subprocess.run(cmd, capture_output=True, text=True)

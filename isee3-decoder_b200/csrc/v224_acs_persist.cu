@@ -56,6 +56,10 @@ __device__ __forceinline__ void st_cs_v2(void *p, uint32_t x, uint32_t y)
 {
     asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void st_cs_b32(void *p, uint32_t x)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+}
 __device__ __forceinline__ void st_v8(void *p, const uint32_t (&v)[8])   // 256-bit store (sm_100+)
 {
     asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
@@ -225,8 +229,9 @@ __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t labe
     // row * 1 MiB + this thread's chunk: one 32 x 32 + 64 multiply-add
     uint32_t *dst;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(dst) : "r"(tab[OPTAB_WORDS + T - 1]), "n"((unsigned)ROWBYTES), "l"(ring_chunk));
-    if (NQ == 4) st_cs_v4(dst, make_uint4(dw[0], dw[1], dw[NQ - 2], dw[NQ - 1]));
-    else         st_cs_v2(dst, dw[0], dw[1]);
+    if (NQ == 4)      st_cs_v4(dst, make_uint4(dw[0], dw[1], dw[NQ - 2], dw[NQ - 1]));
+    else if (NQ == 2) st_cs_v2(dst, dw[0], dw[NQ - 1]);
+    else              st_cs_b32(dst, dw[0]);
     if (threadIdx.x == 0) s0[T] = A[0][0] & 0xffffu;               // slot 0 (tile 0, thread 0) always holds state 0
     if (CAREFUL && T < FK) {
         uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
@@ -258,9 +263,11 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 if (NQ == 4) {
                     const uint4 v = reinterpret_cast<const uint4 *>(xbuf)[e];
                     A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
-                } else {
+                } else if (NQ == 2) {
                     const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
-                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+                    A[mh][0] = v.x - sub; A[mh][NQ - 1] = v.y - sub;
+                } else {
+                    A[mh][0] = xbuf[e] - sub;
                 }
             }
         } else {
@@ -270,9 +277,11 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 if (NQ == 4) {
                     const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)mh * 16 * 65536));
                     A[mh][0] = v.x - sub; A[mh][1] = v.y - sub; A[mh][NQ - 2] = v.z - sub; A[mh][NQ - 1] = v.w - sub;
-                } else {
+                } else if (NQ == 2) {
                     const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(src + (size_t)mh * 16 * 65536));
-                    A[mh][0] = v.x - sub; A[mh][1] = v.y - sub;
+                    A[mh][0] = v.x - sub; A[mh][NQ - 1] = v.y - sub;
+                } else {
+                    A[mh][0] = __ldcg(reinterpret_cast<const uint32_t *>(src + (size_t)mh * 16 * 65536)) - sub;
                 }
             }
         }
@@ -289,8 +298,9 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
 #pragma unroll
         for (int mh = 0; mh < 16; mh++) {
             const uint32_t e = xchg_index(mh * 16 + thr, g);
-            if (NQ == 4) reinterpret_cast<uint4 *>(xbuf)[e] = make_uint4(A[mh][0], A[mh][1], A[mh][NQ - 2], A[mh][NQ - 1]);
-            else         reinterpret_cast<uint2 *>(xbuf)[e] = make_uint2(A[mh][0], A[mh][1]);
+            if (NQ == 4)      reinterpret_cast<uint4 *>(xbuf)[e] = make_uint4(A[mh][0], A[mh][1], A[mh][NQ - 2], A[mh][NQ - 1]);
+            else if (NQ == 2) reinterpret_cast<uint2 *>(xbuf)[e] = make_uint2(A[mh][0], A[mh][NQ - 1]);
+            else              xbuf[e] = A[mh][0];
         }
     }
     bar_compute();
@@ -305,9 +315,11 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             if (NQ == 4) {
                 const uint4 v = reinterpret_cast<const uint4 *>(xbuf)[e];
                 A[ml][0] = v.x; A[ml][1] = v.y; A[ml][NQ - 2] = v.z; A[ml][NQ - 1] = v.w;
-            } else {
+            } else if (NQ == 2) {
                 const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
-                A[ml][0] = v.x; A[ml][1] = v.y;
+                A[ml][0] = v.x; A[ml][NQ - 1] = v.y;
+            } else {
+                A[ml][0] = xbuf[e];
             }
         }
         {
@@ -711,14 +723,17 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
 
 } // namespace V224_NS
 
-#if V224_TILE_COLS_LOG2 == 5
-// The 32-column build is reached from the runtime (compiled against the 64-column headers) through these two entries; the
-// argument structures have the same layout in both namespaces (nothing in them depends on the tile width).
-extern "C" cudaError_t v224_t32_launch_persist(const void *multi_args, cudaStream_t st)
+#ifdef V224_BRIDGE
+// The 32-column builds are reached from the runtime (compiled against the 64-column headers) through two entries each,
+// <V224_BRIDGE>_launch_persist and <V224_BRIDGE>_build_metric_tensor_maps; the argument structures have the same layout in
+// every namespace (nothing in them depends on the tile shape).
+#define V224_CAT2(a, b) a##b
+#define V224_CAT(a, b) V224_CAT2(a, b)
+extern "C" cudaError_t V224_CAT(V224_BRIDGE, _launch_persist)(const void *multi_args, cudaStream_t st)
 {
     return V224_NS::launch_persist(*static_cast<const V224_NS::MultiArgs *>(multi_args), st);
 }
-extern "C" cudaError_t v224_t32_build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why)
+extern "C" cudaError_t V224_CAT(V224_BRIDGE, _build_metric_tensor_maps)(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why)
 {
     return V224_NS::build_metric_tensor_maps(metrics, dev_out, st, why);
 }

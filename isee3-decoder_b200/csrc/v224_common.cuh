@@ -50,8 +50,8 @@ constexpr int FK = 2 * FR;                         // 8 trellis stages per pass
 #define V224_NQ 2
 #endif
 constexpr int NQ = V224_NQ;                        // packed 2x16-bit registers per row per thread
-static_assert(NQ == 2 || NQ == 4, "columns per thread");
-constexpr int COLW_LOG2 = NQ == 2 ? 2 : 3;         // log2(columns per thread)
+static_assert(NQ == 1 || NQ == 2 || NQ == 4, "columns per thread");
+constexpr int COLW_LOG2 = NQ == 1 ? 1 : NQ == 2 ? 2 : 3;   // log2(columns per thread)
 constexpr int COLW = 1 << COLW_LOG2;
 constexpr int FUSED_COLS_LOG2 = V224_TILE_COLS_LOG2;
 static_assert(FUSED_COLS_LOG2 == 6 || FUSED_COLS_LOG2 == 5, "tile width");
@@ -62,7 +62,7 @@ constexpr int FUSED_THREADS   = 16 * FUSED_COLGROUPS;  // 16 row groups x column
 // SM with 64-column tiles, up to 5 CTAs of 192 threads with 32-column tiles; the round-1 -> round-2 exchange buffer is
 // double-buffered (it doubles as the landing zone of the next tile's tensor copy): 3 x 67 KiB / 5 x 35 KiB of shared memory.
 #ifndef V224_CTAS_PER_SM
-#define V224_CTAS_PER_SM (V224_TILE_COLS_LOG2 == 6 ? 3 : 5)
+#define V224_CTAS_PER_SM (V224_TILE_COLS_LOG2 == 6 ? 3 : V224_NQ == 1 ? 3 : 5)
 #endif
 constexpr int FUSED_CTAS_PER_SM = V224_CTAS_PER_SM;
 #ifndef V224_XCHG_BUFS
@@ -87,10 +87,11 @@ constexpr int PSLOTS = 4;                          // in-flight pass bookkeeping
 
 // Decision-row formats (row_fmt[] tags).  0 = canonical (bit index = new-state number, the
 // reference's layout, viterbi224_sse2.c:141,324); 1..8 = written by stage t of a fused pass with 64-column tiles,
-// 9..16 = by stage t - 8 of a fused pass with 32-column tiles, each in that kernel's thread-major layout
+// 9..16 = by stage t - 8 of a fused pass with 32-column tiles (two registers per row and thread), 17..24 = by stage t - 16 of
+// the 32-column build with ONE register per row and thread, each in that kernel's thread-major layout
 // (see fused_bit_address()).
 constexpr uint8_t ROWFMT_CANON = 0;
-constexpr uint8_t ROWFMT_FUSED_BASE = FUSED_COLS_LOG2 == 6 ? 0 : 8;    // tag of stage t = base + t
+constexpr uint8_t ROWFMT_FUSED_BASE = FUSED_COLS_LOG2 == 6 ? 0 : NQ == 2 ? 8 : 16;    // tag of stage t = base + t
 
 // Device-resident control block.  One per decoder handle.  The last CTA of every pass
 // ("resolver") folds the pass's statistics into it; the host only reads it back at the end of
@@ -212,7 +213,13 @@ __host__ __device__ inline uint32_t round2_tid(uint32_t thr, uint32_t g) { retur
 // together land on disjoint banks, and a round-1 thread still writes exactly the rows its own warp read (in place).
 __host__ __device__ inline uint32_t xchg_index(uint32_t m, uint32_t g)
 {
-    if (NQ != 2) return m * FUSED_COLGROUPS + g;
+    if (NQ == 4) return m * FUSED_COLGROUPS + g;
+    if (NQ == 1) {
+        // 64-byte rows of 16 one-word elements: a round-2 warp reads 8 elements (32 bytes) of four rows 16 apart -- odd mh swap
+        // neighbouring rows, mh bit 1 swaps the 32-byte halves: the four pieces land on the four quarters of the banks
+        const uint32_t mh = m >> 4;
+        return (m ^ (mh & 1u)) * FUSED_COLGROUPS + (g ^ ((mh & 2u) << 2));
+    }
     if (FUSED_COLGROUPS == 16) return m * FUSED_COLGROUPS + (g ^ ((m >> 1) & 8u));
     return (m ^ ((m >> 4) & 1u)) * FUSED_COLGROUPS + g;
 }
@@ -229,20 +236,26 @@ constexpr uint32_t FUSED_ROWS_COMPLEMENTED = 1u;
 // butterfly pairs the two rows that differ in bit sb of `inner`, side = that bit, pair index = the other three.
 __host__ __device__ inline uint32_t fused_bit_address(int fmt, uint32_t s)
 {
+    // geometry of the build that wrote the row: 1..8 64-column tiles, 9..16 32-column tiles, 17..24 32-column tiles with one
+    // register per row and thread (all other builds: NQ registers, NQ = this build's)
     const int cols_log2 = fmt > 8 ? 5 : 6;
-    const int t = fmt > 8 ? fmt - 8 : fmt;
-    const uint32_t colgroups = (1u << cols_log2) / COLW, threads = 16 * colgroups;
+    const int nq = fmt > 16 ? 1 : (NQ == 1 ? 2 : NQ);
+    const int t = fmt > 16 ? fmt - 16 : fmt > 8 ? fmt - 8 : fmt;
+    const int colw_log2 = nq == 1 ? 1 : nq == 2 ? 2 : 3;
+    const uint32_t colgroups = (1u << cols_log2) >> colw_log2, threads = 16 * colgroups;
     uint32_t p = ((s >> t) | (s << (23 - t))) & STATEMASK;      // the slot its survivor sits in during the pass
     const uint32_t mh = (p >> 19) & 15, ml = (p >> 15) & 15, j = p & 32767;
-    const uint32_t tile = j >> cols_log2, g = (j & ((1u << cols_log2) - 1)) >> COLW_LOG2;
-    const uint32_t q = (j & (COLW - 1)) >> 1, h = j & 1;
+    const uint32_t tile = j >> cols_log2, g = (j & ((1u << cols_log2) - 1)) >> colw_log2;
+    const uint32_t q = (j & ((1u << colw_log2) - 1)) >> 1, h = j & 1;
     const bool r1 = t <= FR;
     const uint32_t inner = r1 ? mh : ml;
     const uint32_t tid = r1 ? ml * colgroups + g : round2_tid_cg(mh, g, colgroups);
     const int sb = FR - 1 - ((t - 1) % FR);
     const uint32_t side = (inner >> sb) & 1;
     const uint32_t pidx = ((inner >> (sb + 1)) << sb) | (inner & ((1u << sb) - 1));
-    const uint32_t word = (tile * threads + tid) * NQ + side * (NQ / 2) + (q >> 1);
+    if (nq == 1)     // one word per thread and stage: byte = side * 2 + half
+        return (tile * threads + tid) * 32 + ((side << 1) | h) * 8 + pidx;
+    const uint32_t word = (tile * threads + tid) * nq + side * (nq / 2) + (q >> 1);
     return word * 32 + (((q & 1) << 1) | h) * 8 + pidx;
 }
 

@@ -188,6 +188,11 @@ V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *o
             A[ic][q] = f_addmin_u16x2(a, Y, t1);          // min(m2, m3) -> state 2b+1  (:320)
         }
         // gather the sign bits: word = side * NQ/2 + q/2, byte = (q&1)*2 + half, bit = pair index
+        // (one register per row: a single word, byte = side * 2 + half)
+        if (NQ == 1) {
+            const uint32_t s01 = f_prmt(D0[0], D1[0], 0xfdb9);
+            dw[0] = (s01 & (0x01010101u << pidx)) | dw[0];
+        }
 #pragma unroll
         for (int qq = 0; qq < NQ / 2; qq++) {
             const uint32_t s0 = f_prmt(D0[2 * qq], D0[2 * qq + 1], 0xfdb9);

@@ -23,6 +23,10 @@ using namespace v224;
 // the fused pass compiled for 32-column tiles (v224_acs_persist.cu with -DV224_TILE_COLS_LOG2=5, namespace v224t32)
 extern "C" cudaError_t v224_t32_launch_persist(const void *multi_args, cudaStream_t st);
 extern "C" cudaError_t v224_t32_build_metric_tensor_maps(uint16_t *const *metrics, void *dev_out, cudaStream_t st, const char **why);
+#ifdef V224_WITH_Q1
+// A/B builds only: 32-column tiles with one packed register per row and thread (-DV224_NQ=1, namespace v224t32q1); same tensor maps
+extern "C" cudaError_t v224_t32q1_launch_persist(const void *multi_args, cudaStream_t st);
+#endif
 
 namespace {
 
@@ -399,6 +403,10 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
                 const bool t32 = d->tile32 != 0;
                 m.ctx[0] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms, t32 ? d->tmaps32 : d->tmaps, d->optab,
                                        d->len, p, (int)((d->h_ctl->cur + (p - pos) / FK) % NBUF), T_start + p, npasses, d->force_careful};
+#ifdef V224_WITH_Q1
+                if (d->tile32 == 3) { m.grid_limit = d->grid_limit; CU(v224_t32q1_launch_persist(&m, d->stream)); }
+                else
+#endif
                 if (t32) { m.grid_limit = d->grid_limit > 0 ? d->grid_limit : -3; CU(v224_t32_launch_persist(&m, d->stream)); }   // 3 of 5 possible CTAs per SM: measured optimum
                 else CU(launch_persist(m, d->stream));
                 p += npasses * FK;
@@ -465,15 +473,21 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         m.nctx = nctx;
         m.npasses = npasses;
         m.grid_limit = d0->grid_limit > 0 ? d0->grid_limit : (nctx == 1 ? -1 : 0);
+        const bool mt32 = d0->tile32 == 2 || d0->tile32 == 4;        // measurement knobs: lockstep decoders on the 32-column-tile builds
         for (int s = 0; s < nctx; s++) {
             Decoder *d = ds[s];
             d->fused_rows = 1;
             if (grow((void **)&d->optab, &d->optab_cap, passtab_bytes(npasses))) return -1;
-            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], d->tmaps, d->optab, d->len,
-                                   pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
+            m.ctx[s] = PersistArgs{d->ctl, {d->metrics[0], d->metrics[1], d->metrics[2]}, d->ring, d->row_fmt, dev_syms[s], mt32 ? d->tmaps32 : d->tmaps, d->optab,
+                                   d->len, pos, d->h_ctl->cur, T_start[s] + pos, npasses, d->force_careful};
         }
         if (d0->time_kernels) CU(cudaEventRecord(d0->kev0, st));
-        CU(launch_persist(m, st));
+#ifdef V224_WITH_Q1
+        if (d0->tile32 == 4) { m.grid_limit = d0->grid_limit; CU(v224_t32q1_launch_persist(&m, st)); }
+        else
+#endif
+        if (mt32) { m.grid_limit = d0->grid_limit; CU(v224_t32_launch_persist(&m, st)); }
+        else CU(launch_persist(m, st));
         if (d0->time_kernels) CU(cudaEventRecord(d0->kev1, st));
         d0->launches += 2 * nctx + 1;
         for (int s = 0; s < nctx; s++) {
