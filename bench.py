@@ -5,7 +5,7 @@
 
 One "step" = one complete decode of the workload's soft-symbol stream through the streaming path of vdecode.c (the symbol
 pairing / phase flip of vdecode.c:101-140 on the host, then update + decodebit(delay, state 0) per pair, vdecode.c:145-152)
-in block form: fused 8-stage ACS passes + batched tracebacks, per GPU 3 decoders that one persistent kernel advances in
+in block form: fused 8-stage ACS passes + batched tracebacks, per GPU 4 decoders that one persistent kernel advances in
 lockstep over contiguous segments (every hand-over verified on the device, output identical to the sequential decode).
 
   config 2 (default) : symdemod-format telemetry stream at 3 dB, decode delay 200, odd junk prefix (automatic phase flip).
@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 
 DELAY = 200                     # vdecode default decode delay (vdecode.c:44)
 BLOCK = 8192                    # stages per update batch; ring = BLOCK + DELAY rows (8.2 GiB)
-SEGMENTS = 3                    # per GPU: decoders advanced in lockstep over contiguous segments of the rank's range
+SEGMENTS = 4                    # per GPU: decoders advanced in lockstep over contiguous segments of the rank's range
 CONV = 2048                     # stages a late-started decoder gets to converge before its verified hand-over
 SEED = 20141
 JUNK = 101                      # config 2: odd junk prefix, vdecode starts on the wrong symbol phase

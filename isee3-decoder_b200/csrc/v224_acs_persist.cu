@@ -175,7 +175,7 @@ struct TileInfo {
     int careful;
     int n, s;            // pass and decoder (the protocol warps' own bookkeeping)
     uint32_t lab;        // packed_tile_labels(tau): the tile's part of every stage's branch label
-    int pad;
+    int discard;         // the pass cannot be invalidated: its input lines may be dropped from the L2 once they are in shared memory
 };
 // Tile k of a CTA uses bookkeeping slot k % NSLOT (info, pass table, full/done barriers) and data buffer k % XCHG_BUFS.
 // A data buffer is free again as soon as the tile's round-2 reads are over (`freeb`), long before its stores are out
@@ -367,6 +367,12 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
 // ------------------------------------------------------------------------------------------
 // protocol warp
 // ------------------------------------------------------------------------------------------
+// 64-column build only: a decoder alone (32-column build) keeps its three buffers in the L2 anyway
+#ifndef V224_DISCARD_INPUT
+#define V224_DISCARD_INPUT (V224_TILE_COLS_LOG2 == 6)
+#endif
+constexpr bool DISCARD_INPUT = V224_DISCARD_INPUT;
+static_assert(!DISCARD_INPUT || FUSED_TILE_COLS == 64, "a discarded line is 128 bytes = one tile's piece of a metric row");
 constexpr unsigned SPIN_LIMIT = 20u * 1000u * 1000u;      // polls of >= 20-40 ns: seconds.  A wait that long means a broken invariant.
 
 __device__ __forceinline__ void slot_reset(PassSlot &s, int pass)
@@ -375,20 +381,21 @@ __device__ __forceinline__ void slot_reset(PassSlot &s, int pass)
     s.done_word = done_word_fresh(pass);          // no tile done yet, tagged with the pass the slot now serves
 }
 
-__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T)
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T, int no_discard)
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
     pc.resolved_upto = 0;
     pc.npasses = npasses;
     pc.force_careful = force_careful;
+    pc.no_discard = no_discard;
     pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
     pc.maxR_prev = c->maxR;
     for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i], i); pc.slot[i].pass_word = 0; }
     const int careful0 = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
     const int careful1 = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
-    pc.slot[0].pass_word = make_pass_word(0, careful0, c->sub);
-    pc.slot[1].pass_word = make_pass_word(1, careful1, 0);
+    pc.slot[0].pass_word = make_pass_word(0, careful0, c->sub, !no_discard && discard_ok(c->maxR, c->spread, FK));
+    pc.slot[1].pass_word = make_pass_word(1, careful1, 0, !no_discard && discard_ok(c->maxR, c->spread, 2 * FK));
     int stop = npasses;
     if (c->spread > MAX_FAST_SPREAD || c->error || c->T != expected_T) stop = 0;
     // non-careful passes are not validated stage by stage: keep them well away from saturation
@@ -409,8 +416,8 @@ __device__ void resolve_persist(Ctl *c, int n)
     }
     PassSlot &sl = pc.slot[n % PSLOTS];
     const unsigned long long pw = *(volatile unsigned long long *)&sl.pass_word;
-    const bool careful = (pw >> 31) & 1u;
-    const int sub = (int)(pw & 0x7fffffffu);
+    const bool careful = pass_word_careful(pw);
+    const int sub = pass_word_sub(pw);
     bool valid = !c->error && n < *(volatile int *)&pc.stop_pass;
     long long O = pc.Ostore + sub;                     // offset of the values this pass loaded
     long long maxR = pc.maxR_prev;                     // exact at pass start; +510 per stage bounds it inside
@@ -452,13 +459,15 @@ __device__ void resolve_persist(Ctl *c, int n)
         // parameters of pass n+2 (its slot is free: pass n-2 is long resolved)
         PassSlot &nx = pc.slot[(n + 2) % PSLOTS];
         slot_reset(nx, n + 2);
-        const int sub1 = (int)(*(volatile unsigned long long *)&pc.slot[(n + 1) % PSLOTS].pass_word & 0x7fffffffu);
+        const int sub1 = pass_word_sub(*(volatile unsigned long long *)&pc.slot[(n + 1) % PSLOTS].pass_word);
         const int careful2 = pc.force_careful || ((long long)z + O + 510ll * 2 * FK >= RENORM_TRIGGER);
         if (!careful2 && (long long)mx + O + 510ll * 2 * FK > 32767) {
             if (n + 2 < pc.stop_pass) pc.stop_pass = n + 2;
         }
         __threadfence();                                                   // the reset slot before the word that opens it
-        *(volatile unsigned long long *)&nx.pass_word = make_pass_word(n + 2, careful2, (int)mn - sub1);   // sub <= min of pass n+1's output
+        // (the statistics are pass n's: pass n+2 ends 2 * FK stages later)
+        const int discard2 = !pc.no_discard && discard_ok((long long)mx + O, (long long)mx - mn, 2 * FK);
+        *(volatile unsigned long long *)&nx.pass_word = make_pass_word(n + 2, careful2, (int)mn - sub1, discard2);   // sub <= min of pass n+1's output
     } else {
         // the pass (and anything that already consumed its output) is discarded; its input buffer is intact
         if (n < pc.stop_pass) { pc.stop_pass = n; c->n_invalidated++; }
@@ -551,8 +560,9 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
             ti.ring = a.ring;
             ti.st = &pc.slot[n % PSLOTS].st;
             ti.tau = tau;
-            ti.sub2 = (uint32_t)(pw & 0x7fffffffu) * 0x10001u;
-            ti.careful = (int)((pw >> 31) & 1u);
+            ti.sub2 = (uint32_t)pass_word_sub(pw) * 0x10001u;
+            ti.careful = (int)pass_word_careful(pw);
+            ti.discard = (int)pass_word_discard(pw);
             ti.go = stopped ? 0 : 1;
             ti.n = n;
             ti.s = (int)s;
@@ -585,6 +595,17 @@ __device__ void retirer_warp(FusedSmem &sm, const MultiArgs &m)
         const int go = ti.go, n = ti.n, s = ti.s;
         const unsigned tau = ti.tau;
         if (go < 0) return;
+        if (DISCARD_INPUT && BULK_LOAD && go > 0 && ti.discard) {
+            // The tile's input is in shared memory now (the hand-over completed with the tensor copy's bytes), and every
+            // 2 * FUSED_TILE_COLS-byte piece of a metric row is read by exactly ONE tile: the 256 lines are dead.  With several
+            // decoders in lockstep their buffers do not fit the L2 together, and dead lines would be written back to HBM when
+            // they are evicted -- 16.6 MB of the 25 MB a pass writes, 100 W of the board's 1000 W (profiles/r02_ab_discard.txt).
+            // Only for passes that cannot be invalidated (pass_word): an invalidated pass is run again from this very input.
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(ti.oldm) + (size_t)tau * FUSED_TILE_COLS * 2;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (size_t)(k * 32 + lane) * 65536) : "memory");
+        }
         mbar_wait_proto(&sm.done[b], par);         // every compute warp has issued the tile's stores and is done with the slot
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.slotfree[b]);
@@ -713,7 +734,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     for (int s = 0; s < m.nctx; s++) {
         const PersistArgs &a = m.ctx[s];
         k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
-        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0);
+        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0, m.no_discard);
     }
     const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
     const int grid = (int)(items < nslots ? items : nslots);

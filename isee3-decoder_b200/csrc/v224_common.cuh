@@ -134,15 +134,29 @@ __host__ __device__ inline unsigned stats_max(const PassStats &s)
 // warp has to poll, so that one round of parallel loads decides "may this tile start":
 //   done_word = [63:24] tiles done per class, 10 bits each (class = tile index mod TILE_CLASSES) | [23:11] pass number mod 2^13
 //               | [10:0] tiles done      (the pass tag is written when the slot is reset for that pass)
-//   pass_word = (pass number + 1) << 32 | careful << 31 | sub     published by the resolver of pass n-2 (or the launch)
+//   pass_word = (pass number + 1) << 32 | careful << 31 | discard << 30 | sub     published by the resolver of pass n-2 (or the launch)
+//               discard: the pass cannot be invalidated (the launch / resolver has proved that the reference cannot saturate before it
+//               ends and that its metric spread stays in range), so its tiles may drop their input lines from the L2
 struct PassSlot {
     PassStats st;
     unsigned long long done_word;
     unsigned long long pass_word;
 };
-__host__ __device__ inline unsigned long long make_pass_word(int n, int careful, int sub)
+__host__ __device__ inline unsigned long long make_pass_word(int n, int careful, int sub, int discard = 0)
 {
-    return ((unsigned long long)(unsigned)(n + 1) << 32) | ((unsigned long long)(careful ? 1u : 0u) << 31) | (unsigned)sub;
+    return ((unsigned long long)(unsigned)(n + 1) << 32) | ((unsigned long long)(careful ? 1u : 0u) << 31) |
+           ((unsigned long long)(discard ? 1u : 0u) << 30) | ((unsigned)sub & 0x3fffffffu);
+}
+__host__ __device__ inline int pass_word_sub(unsigned long long w) { return (int)(w & 0x3fffffffu); }
+__host__ __device__ inline bool pass_word_careful(unsigned long long w) { return ((w >> 31) & 1u) != 0; }
+__host__ __device__ inline bool pass_word_discard(unsigned long long w) { return ((w >> 30) & 1u) != 0; }
+// A pass may drop its input lines only if nothing can invalidate it: the reference cannot saturate before the pass ends (the
+// largest metric grows by at most 510 per stage; non-careful passes are not even started otherwise) and the spread, which also
+// grows by at most 510 per stage, stays below the fast path's limit (`stages_ahead` = stages between the statistics maxR and
+// spread come from and the end of the pass).
+__host__ __device__ inline int discard_ok(long long maxR, long long spread, int stages_ahead)
+{
+    return maxR + 510ll * stages_ahead <= 32767 && spread + 510ll * stages_ahead <= MAX_FAST_SPREAD;
 }
 __host__ __device__ inline unsigned done_class_count(unsigned long long w, unsigned cls) { return (unsigned)(w >> (24 + 10 * cls)) & 0x3ffu; }
 __host__ __device__ inline unsigned long long done_increment(unsigned cls) { return 1ull | (1ull << (24 + 10 * cls)); }
@@ -156,7 +170,7 @@ struct PersistCtl {
     int stop_pass;          // passes >= stop_pass must not run (saturation watch / invalidated pass)
     int npasses;
     int force_careful;
-    int pad;
+    int no_discard;         // passes never drop their consumed input lines from the L2 (option)
     long long Ostore;       // R = P_stored + Ostore for the output of the last resolved pass
     long long maxR_prev;    // largest reference metric at the output of the last resolved pass
     PassSlot slot[PSLOTS];

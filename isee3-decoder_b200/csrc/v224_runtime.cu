@@ -144,6 +144,7 @@ struct Decoder {
     int spec_valid;            // the last stage carried the walk for (spec_delay, spec_end) at stage counter spec_T
     long long spec_T, spec_bit;
     int no_mailbox;            // option: always take the synchronous path
+    int no_discard;            // option: fused passes never drop their consumed input lines from the L2
     int slow_single;           // option: the scalar form of the one-stage kernel
     int fused_rows;            // a fused pass has written rows into the ring since it was last cleared (their layout differs)
     // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
@@ -341,6 +342,7 @@ int recycle(Decoder *d)
     d->force_single = d->force_sat = d->force_careful = d->per_pass_launch = d->no_walk_cache = d->grid_limit = d->no_mailbox = 0;
     d->spec_want = d->spec_valid = 0;
     d->slow_single = 0;
+    d->no_discard = 0;
     d->fused_rows = 0;                       // every row it ever wrote is cleared below, tags included
     d->tile32 = TILE32_DEFAULT;
     d->chain_seg = 64;
@@ -395,6 +397,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
                 MultiArgs m;
                 m.nctx = 1;
                 m.npasses = npasses;
+                m.no_discard = d->no_discard;
                 // a decoder alone is latency bound (pass n+1 needs all of pass n).  64-column tiles: one CTA per SM finishes a tile
                 // sooner than three sharing the SM, and the pass with it (13.6 instead of 15.3 us); 32-column tiles (the default
                 // for a lone decoder): half the tile latency and finer dependencies, 12.9 us (profiles/r02_probe_*.txt)
@@ -472,6 +475,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         MultiArgs m;
         m.nctx = nctx;
         m.npasses = npasses;
+        m.no_discard = d0->no_discard;
         m.grid_limit = d0->grid_limit > 0 ? d0->grid_limit : (nctx == 1 ? -1 : 0);
         const bool mt32 = d0->tile32 == 2 || d0->tile32 == 4;        // measurement knobs: lockstep decoders on the 32-column-tile builds
         for (int s = 0; s < nctx; s++) {
@@ -1399,7 +1403,7 @@ int v224x_multi_stream_decode(v224x_multi *m, const unsigned char *syms, long lo
 {
     if (!m || !syms || !bits_out) { set_err("v224x_multi_stream_decode: NULL argument"); return -1; }
     if (nbits <= 0) { if (rep) memset(rep, 0, sizeof *rep); return 0; }
-    return multi_core(m, syms, nbits, delay, bits_out, nseg <= 0 ? 3 : nseg, conv, rep);
+    return multi_core(m, syms, nbits, delay, bits_out, nseg <= 0 ? 4 : nseg, conv, rep);
 }
 
 void v224x_trim(void)
@@ -1602,6 +1606,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "no_mailbox")) d->no_mailbox = (int)value;
     else if (!strcmp(key, "tile32")) d->tile32 = (int)value;
     else if (!strcmp(key, "slow_single")) d->slow_single = (int)value;
+    else if (!strcmp(key, "no_discard")) d->no_discard = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

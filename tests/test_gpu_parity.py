@@ -53,7 +53,7 @@ def test_golden_default_path(golden_cases, name):
                                   {"chain_seg": 64, "chain_warm": 16},
                                   {"tile32": 1}, {"tile32": 0}, {"tile32": 1, "force_careful": 1}, {"tile32": 1, "per_pass_launch": 1},
                                   {"tile32": 1, "grid_limit": 97}, {"no_mailbox": 1}, {"slow_single": 1},
-                                  {"tile32": 2}])
+                                  {"tile32": 2}, {"no_discard": 1}, {"tile32": 0, "grid_limit": 444}])
 @pytest.mark.parametrize("name", ["awgn1db_648_chunks", "erasure_304", "ringwrap_len40_200", "saturation_forced_72", "stream_d64_320"])
 def test_golden_kernel_variants(golden_cases, name, opts):
     case = golden_cases[name]
@@ -807,3 +807,44 @@ def test_stock_hybridtest_runs_on_the_gpu_library():
     got_l, want_l = lines(out.stdout), lines(want)
     assert got_l == want_l, [(a, b) for a, b in zip(got_l, want_l) if a != b][:3]
     assert "Viterbi attempts 15 good frames: 11 frame errors 4" in out.stdout
+
+
+def test_two_host_threads_decode_concurrently_on_one_gpu():
+    """The library is used from several host threads at once by the multi-GPU context (one thread per GPU) and may be by callers:
+    two threads, each with its own handle on the same GPU, run segmented stream decodes, frame decodes and create / delete cycles
+    at the same time; every result equals the single-threaded one (launch geometry cache, tensor-map encoder, decoder and ring
+    pools are shared state)."""
+    import threading
+    n, delay = 40_000, 100
+    streams = [S.telemetry_stream(n, 3.0, seed=700 + i)[1] for i in range(2)]
+    want = []
+    for syms in streams:
+        with v224.Viterbi224(delay + 2048) as d:
+            d.init(0)
+            want.append(d.stream_decode(syms, delay)[0])
+    got = [None, None]
+    errors = []
+
+    def work(i):
+        try:
+            for rep in range(3):
+                with v224.Viterbi224(delay + 2048) as d:          # create / delete every round: the pools are exercised too
+                    d.init(0)
+                    out, rep_ = d.stream_decode_seg(streams[i], delay, 3, 1024)
+                    assert rep_["redone"] == 0
+                    data, fs = S.vtest_frame(512, 3.0, seed=900 + i)
+                    d.init(0)
+                    d.update_blk(fs, 512)
+                    assert np.array_equal(d.chainback(512, 0), data)
+                got[i] = out
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for i in range(2):
+        assert np.array_equal(got[i], want[i]), i

@@ -6,8 +6,8 @@ timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytes
 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "bench ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-side-rooflines > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 120 python tools/prof_multi.py default 3 2048 > gpurun_out/prof_multi_plain.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_acs_persist -s 1 -c 1 -o gpurun_out/r02_k_acs_persist_3dec python tools/prof_multi.py default 3 2048 > gpurun_out/ncu_full.log 2>&1
+timeout 120 python tools/prof_multi.py default 4 2048 > gpurun_out/prof_multi_plain.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_acs_persist -s 1 -c 1 -o gpurun_out/r02_k_acs_persist_4dec python tools/prof_multi.py default 4 2048 > gpurun_out/ncu_full.log 2>&1
 timeout 120 python tools/prof_single.py alone 2048 > gpurun_out/prof_alone_plain.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_acs_persist -s 1 -c 1 -o gpurun_out/r02_k_acs_persist_alone_t32 python tools/prof_single.py alone 2048 > gpurun_out/ncu_full_alone.log 2>&1
 timeout 120 python tools/prof_single.py stage 512 > gpurun_out/prof_stage_plain.log 2>&1 && \
