@@ -15,7 +15,8 @@
 // Extra options: -B pairs  block size (default 262144 per GPU; latency = one block), -S n  decoders in lockstep per GPU (default 4),
 // -G n  GPUs: every block is cut into n time segments decoded side by side, one per GPU (v224x_multi_stream_decode: every
 // GPU-to-GPU hand-over verified on the device, a range whose decoder had not converged is decoded again -- the output
-// is the one-GPU output), -v  a summary of the hand-over checks on stderr at the end,
+// is the one-GPU output), -D a,b,..  the CUDA device ordinals to use with -G (default 0 .. n-1; an ordinal may repeat: its
+// ranges then share that GPU), -v  a summary of the hand-over checks on stderr at the end,
 // -P  pairs only: write the symbol pairs that would go to the decoder (2 bytes each) to stdout and exit -- no GPU needed;
 // the CPU test tier checks the pairing / phase-flip logic through it.
 // -f  frames instead of bits: standard output is what `vdecode | framer` prints (framer.c:61-95: a 1024-bit shift
@@ -60,11 +61,12 @@ int main(int argc, char *argv[])
 {
     int delay = 200, interval = 1024, quiet = 0, dontflip = 0, phase = 0, nseg = 4, pairs_only = 0, framing = 0, bitrate = 512, bits_in = 0;
     int ngpu = 1, verbose = 0;
+    const char *devlist = nullptr;
     long block = 0;
     const char *lang = getenv("LANG");
     setlocale(LC_ALL, lang ? lang : "en_US.utf8");                       // vdecode.c:59-62 (thousands separators in the status line)
     int opt;
-    while ((opt = getopt(argc, argv, "d:pi:qFB:S:Pfr:bG:v")) != -1) {
+    while ((opt = getopt(argc, argv, "d:pi:qFB:S:Pfr:bG:vD:")) != -1) {
         switch (opt) {
         case 'F': dontflip = 1; break;
         case 'q': quiet = 1; break;
@@ -79,6 +81,7 @@ int main(int argc, char *argv[])
         case 'r': bitrate = atoi(optarg); break;
         case 'G': ngpu = atoi(optarg); break;
         case 'v': verbose = 1; break;
+        case 'D': devlist = optarg; break;
         default: break;
         }
     }
@@ -96,7 +99,14 @@ int main(int argc, char *argv[])
     v224x_multi *vm = nullptr;
     if (!pairs_only && !(framing && bits_in)) {
         if (ngpu > 1) {
-            vm = v224x_multi_create(nullptr, ngpu, ring_rows);
+            std::vector<int> devs;
+            for (const char *q = devlist; q && *q;) {
+                devs.push_back(atoi(q));
+                q = strchr(q, ',');
+                if (q) q++;
+            }
+            if (!devs.empty() && (int)devs.size() != ngpu) { fprintf(stderr, "%s: -D lists %zu devices, -G says %d\n", argv[0], devs.size(), ngpu); return 1; }
+            vm = v224x_multi_create(devs.empty() ? nullptr : devs.data(), ngpu, ring_rows);
             if (!vm) { fprintf(stderr, "%s: v224x_multi_create failed: %s\n", argv[0], v224x_last_error()); return 1; }
             v224x_multi_init(vm, 0);
         } else {

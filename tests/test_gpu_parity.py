@@ -663,6 +663,14 @@ def test_config2_at_scale_equals_the_unmodified_reference():
     got = np.frombuffer(out.stdout, dtype=np.uint8) - ord("0")
     assert got.size == want.size and np.array_equal(got, want), f"{int((got[:want.size] != want[:got.size]).sum())} bits differ from the reference's output"
     assert _status_lines(out.stderr) == [ln.split(": ", 1)[1].encode() for ln in want_err.splitlines() if ": " in ln]
+    # (1b) the same program over two GPUs (-G 2; on a one-GPU box both ranges on device 0), blocks of 40,000 pairs: same stdout, and
+    #      the hand-over summary says every GPU-to-GPU hand-over was verified
+    ndev = v224.device_count()
+    out2 = subprocess.run([blk, "-d", str(g.DELAY), "-q", "-B", "40000", "-S", "2", "-G", "2", "-D", f"0,{1 % ndev}", "-v"], input=soft.tobytes(),
+                          capture_output=True, timeout=600, env=env)
+    assert out2.returncode == 0, out2.stderr[-400:]
+    assert out2.stdout == out.stdout
+    assert b"GPU-to-GPU hand-overs verified 2, ranges redone 0" in out2.stderr and b"worst snapshot spread 0" in out2.stderr, out2.stderr[-300:]
     # (2)
     pairs, flips = v224.pair_symbols(soft)
     assert len(flips) == 2
@@ -673,7 +681,6 @@ def test_config2_at_scale_equals_the_unmodified_reference():
         assert rep["segments"] == 3 and rep["redone"] == 0
     assert np.array_equal(bits[g.DELAY:], want)
     # (3)
-    ndev = v224.device_count()
     with v224.MultiGpu(2, g.DELAY + 4096, devices=[0, 1 % ndev]) as m:
         m.init(0)
         mbits, mrep = m.stream_decode(pairs.reshape(-1), g.DELAY, nseg=2, conv=2048)
