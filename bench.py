@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- decoded bits/s of the B200 viterbi224 decoder on BASELINE.json's workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|4|5] [--total-bits B] [--scaling strong|weak] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--total-bits B] [--scaling strong|weak] [--impl reference]
 
 One "step" = one complete decode of the workload's soft-symbol stream through the streaming path of vdecode.c (the symbol
 pairing / phase flip of vdecode.c:101-140 on the host, then update + decodebit(delay, state 0) per pair, vdecode.c:145-152)
@@ -11,6 +11,7 @@ lockstep over contiguous segments (every hand-over verified on the device, outpu
   config 2 (default) : symdemod-format telemetry stream at 3 dB, decode delay 200, odd junk prefix (automatic phase flip).
                        N = 1: 1,048,576 bits (BASELINE's size).  N > 1: ONE fixed stream of 8,388,608 bits cut into N time
                        segments (strong scaling; --scaling weak: 1,048,576 bits per GPU, --total-bits to change the stream)
+  config 3           : 4,194,304 bits, vtest-style AWGN at 2 dB, decode delay 2048 (long traceback, late survivor merge)
   config 4           : 16,777,216 bits, vtest-style AWGN at 1 dB (no frame structure: pairs as received, vdecode -F)
   config 5           : one long stream generated on the GPUs (N > 1: 268,435,456 bits; N = 1: 33,554,432 bits unless --total-bits
                        says otherwise; 2^24-bit blocks keyed by seed and block index, symdemod format at 3 dB), strong scaling
@@ -57,6 +58,8 @@ B_STAGE_UNFUSED = 34603010                             # bytes per decoded bit o
 CONFIGS = {
     2: {"bits_n1": 1 << 20, "bits_multi": 1 << 23, "ebn0": 3.0, "style": "symdemod telemetry (1024-bit minor frames, sync word), odd junk prefix",
         "pairing": "vdecode.c:101-140 sync correlator, automatic phase flip"},
+    3: {"bits_n1": 1 << 22, "bits_multi": 1 << 22, "ebn0": 2.0, "delay": 2048, "style": "vtest-style AWGN, random data, long decode delay (late survivor merge)",
+        "pairing": "as received (vdecode -F)"},
     4: {"bits_n1": 1 << 24, "bits_multi": 1 << 24, "ebn0": 1.0, "style": "vtest-style AWGN, random data", "pairing": "as received (vdecode -F)"},
     5: {"bits_n1": 1 << 25, "bits_multi": 1 << 28, "ebn0": 3.0, "style": "symdemod-format AWGN, random data, generated on the GPU",
         "pairing": "as received (vdecode -F)"},
@@ -129,10 +132,10 @@ def host_stream(config, total_bits):
     S = v224.streams
     if config == 2:
         return S.telemetry_stream(total_bits, CONFIGS[2]["ebn0"], seed=SEED, junk_symbols=JUNK)
-    rng = np.random.default_rng(SEED + 4)
+    rng = np.random.default_rng(SEED + config)
     bits = rng.integers(0, 2, total_bits, dtype=np.uint8)
     sym01, _ = S.encode_bits(bits, 0)
-    return bits, S.awgn_vtest(sym01, CONFIGS[4]["ebn0"], rng)
+    return bits, S.awgn_vtest(sym01, CONFIGS[config]["ebn0"], rng)
 
 
 GEN_BLOCK = 1 << 24     # config 5: the stream's generation unit (bits)
@@ -410,7 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--total-bits", type=int, default=0, help="length of the stream (default: the config's size; N > 1: the fixed strong-scaling stream)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: one fixed stream (strong) or 1 Mi bits per GPU (weak)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -418,6 +421,8 @@ def main():
     ap.add_argument("--segments", type=int, default=SEGMENTS, help="decoders advanced in lockstep per GPU (1 = sequential)")
     ap.add_argument("--native-multi", type=int, default=0, help="one process, this many GPUs through v224x_multi_stream_decode")
     args = ap.parse_args()
+    global DELAY
+    DELAY = CONFIGS[args.config].get("delay", DELAY)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(SINGLE_FAST_THREADS, 2) k_acs_single_fast(Sing
         return;
     }
     const long long T0 = c->T;
-    if (blockIdx.x == gridDim.x - 1 && a.spec_walk) {
-        // Walker block (per-bit streaming): the decodebit walk the caller is about to ask for (vdecode.c:152) starts at new
+    if (blockIdx.x == 0 && a.spec_walk) {
+        // Walker block (per-bit streaming; block 0, so that it is resident from the start): the decodebit walk the caller is about to ask for (vdecode.c:152) starts at new
         // state spec_end of THIS row and from there on only reads older rows.  It waits for that one decision (the thread
         // that computes it publishes it, tagged with the stage) and walks while the other blocks are still working.
         if (threadIdx.x == 0) {
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(SINGLE_FAST_THREADS, 2) k_acs_single_fast(Sing
         return;
     }
     const uint32_t nwork = gridDim.x - (a.spec_walk ? 1u : 0u);    // blocks that share the stage's units
+    const uint32_t wblock = blockIdx.x - (a.spec_walk ? 1u : 0u);  // this block's index among them
     const uint32_t sub2 = (uint32_t)c->sub * 0x10001u;
     const uint16_t *oldm = a.metrics[c->cur];
     uint16_t *newm = a.metrics[(c->cur + 1) % NBUF];
@@ -369,8 +370,8 @@ __global__ void __launch_bounds__(SINGLE_FAST_THREADS, 2) k_acs_single_fast(Sing
         X0[i] = x[0] | (x[1] << 16);
     }
     // this block's units: warp-aligned, the same count (+-32) for every block
-    const uint32_t wu0 = (uint32_t)(((unsigned long long)blockIdx.x * (NUNITS / 32)) / nwork) * 32u;
-    const uint32_t wu1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * (NUNITS / 32)) / nwork) * 32u;
+    const uint32_t wu0 = (uint32_t)(((unsigned long long)wblock * (NUNITS / 32)) / nwork) * 32u;
+    const uint32_t wu1 = (uint32_t)(((unsigned long long)(wblock + 1) * (NUNITS / 32)) / nwork) * 32u;
     uint32_t mnp = 0xffffffffu, mxp = 0;
     const uint4 *old4 = reinterpret_cast<const uint4 *>(oldm);
     for (uint32_t base = wu0; base < wu1; base += 2 * SINGLE_FAST_THREADS) {
@@ -526,6 +527,26 @@ __global__ void k_stream_trace(TraceArgs a, long long T_first, int nout, int del
     bits_out[i] = (uint8_t)bit;
 }
 
+// The same for up to MAX_CTX decoders in ONE launch.  A walk is a chain of `delay` dependent loads (latency bound, ~0.7 us per
+// step): the lockstep decoders' tracebacks of one chunk of stages are independent chains, so they share one launch instead of
+// running one after the other (4 launches of 140 us each at delay 200 -> one).
+__global__ void k_stream_trace_multi(StreamTraceMulti m)
+{
+    const StreamTraceJob &j = m.job[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= j.nout) return;
+    long long t = j.T_first + i + 1;
+    uint32_t st = 0;
+    uint32_t bit = 0;
+    for (int s = 0; s < m.delay; s++) {
+        --t;
+        if (t < 0) { bit = 0; break; }
+        bit = read_decision(j.a.ring, j.a.row_fmt, t % j.a.len, st);
+        st = (bit << (K - 2)) | (st >> 1);
+    }
+    j.bits_out[i] = (uint8_t)bit;
+}
+
 // ------------------------------------------------------------------------------------------
 // reductions / export
 // ------------------------------------------------------------------------------------------
@@ -635,7 +656,7 @@ cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)
 {
     if (sat) { k_acs_single<true><<<NBFLY / 8 / 256, 256, 0, st>>>(a); return cudaGetLastError(); }
     if (a.slow_form) { k_acs_single<false><<<NBFLY / 8 / 256, 256, 0, st>>>(a); return cudaGetLastError(); }
-    // two blocks of 512 threads per SM, all resident at once
+    // two blocks of 512 threads per SM, all resident at once (with a speculative walk block 0 walks and the others share the units)
     static int sms_of[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -644,7 +665,7 @@ cudaError_t launch_single(const SingleArgs &a, bool sat, cudaStream_t st)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         if (dev >= 0 && dev < 64) sms_of[dev] = sms;                 // (a benign race: every thread stores the same value)
     }
-    k_acs_single_fast<<<2 * sms + (a.spec_walk ? 1 : 0), SINGLE_FAST_THREADS, 0, st>>>(a);
+    k_acs_single_fast<<<2 * sms, SINGLE_FAST_THREADS, 0, st>>>(a);     // all resident at once, the walker block (if any) included
     return cudaGetLastError();
 }
 cudaError_t launch_chainback(const TraceArgs &a, uint32_t nbits, uint32_t endstate, int L, int warm, uint8_t *out, uint32_t *seg_guess,
@@ -671,6 +692,14 @@ cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout,
 {
     if (nout <= 0) return cudaSuccess;
     k_stream_trace<<<(nout + 63) / 64, 64, 0, st>>>(a, T_first, nout, delay, bits_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_stream_trace_multi(const StreamTraceMulti &m, cudaStream_t st)
+{
+    int most = 0;
+    for (int k = 0; k < m.njobs; k++) most = m.job[k].nout > most ? m.job[k].nout : most;
+    if (most <= 0 || m.njobs <= 0) return cudaSuccess;
+    k_stream_trace_multi<<<dim3((most + 63) / 64, m.njobs), 64, 0, st>>>(m);
     return cudaGetLastError();
 }
 cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st)

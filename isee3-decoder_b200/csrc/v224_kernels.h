@@ -86,6 +86,10 @@ cudaError_t launch_walk(const TraceArgs &a, long long dp, int delay, uint32_t en
 cudaError_t launch_walk_incremental(const TraceArgs &a, long long T, long long prev_T, int delay, uint32_t endstate, uint32_t *cache,
                                     unsigned long long *result, unsigned *steps_out, cudaStream_t st);
 cudaError_t launch_stream_trace(const TraceArgs &a, long long T_first, int nout, int delay, uint8_t *bits_out, cudaStream_t st);
+// the streaming tracebacks of several lockstep decoders in one launch
+struct StreamTraceJob { TraceArgs a; long long T_first; int nout; uint8_t *bits_out; };
+struct StreamTraceMulti { int njobs, delay; StreamTraceJob job[MAX_CTX]; };
+cudaError_t launch_stream_trace_multi(const StreamTraceMulti &m, cudaStream_t st);
 cudaError_t launch_argmin(const uint16_t *m, unsigned long long *key, cudaStream_t st);
 cudaError_t launch_minmax(const uint16_t *m, unsigned *mnmx, cudaStream_t st);
 cudaError_t launch_metric_diff(const uint16_t *a, const uint16_t *b, int *out2, cudaStream_t st);

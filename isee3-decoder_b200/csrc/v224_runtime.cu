@@ -228,6 +228,7 @@ int mailbox_wait(Decoder *d)
     if (mb->declined) { set_err("per-bit stage declined to run (stage %lld)", d->h_ctl->T); return -1; }
     memcpy(d->h_ctl, mb->ctl_head, CTL_HOST_BYTES);
     d->spec_bit = mb->walk_bit;
+    if (d->spec_valid && d->spec_bit < -1) { d->spec_valid = 0; d->cache_valid = 0; }      // the walker gave up: its cache entries cannot be trusted
     if (d->h_ctl->error) { set_err("device control block reports invariant violation %d", d->h_ctl->error); return -1; }
     return 0;
 }
@@ -683,13 +684,18 @@ int seg_core(Decoder *d, const uint8_t *dev_syms, int nbits, int delay, uint8_t 
         const uint8_t *sp[MAX_CTX];
         for (int i = 0; i < S; i++) sp[i] = sy[i] + 2 * (size_t)a;
         if (multi_update_core(D, sp, S, b - a, nullptr)) return -1;
+        StreamTraceMulti tm;
+        tm.njobs = 0;
+        tm.delay = delay;
         for (int i = 0; i < S; i++) {
             // decoder i >= 1 emits nothing inside its warm-up, nobody inside the range's
             const int o0 = std::max(std::max(a, i ? W : 0), lead - i * A);
-            if (o0 < b) {
-                CU(launch_stream_trace(trace_args(D[i]), T0[i] + o0, b - o0, delay, dev_bits + ((size_t)i * A + o0 - lead), st));
-                d->launches++;
-            }
+            if (o0 < b) tm.job[tm.njobs++] = StreamTraceJob{trace_args(D[i]), T0[i] + o0, b - o0, dev_bits + ((size_t)i * A + o0 - lead)};
+        }
+        if (tm.njobs) {
+            // the decoders' tracebacks are independent chains of dependent loads: one launch for all of them
+            CU(launch_stream_trace_multi(tm, st));
+            d->launches++;
         }
         if (b == check_early)
             for (int i = 1; i < S; i++) CU(cudaMemcpyAsync(D[i]->snap, D[i]->metrics[D[i]->h_ctl->cur], METRICBYTES, cudaMemcpyDeviceToDevice, st));
