@@ -208,6 +208,14 @@ __global__ void __launch_bounds__(PASSTAB_WORDS) k_build_passtab(uint32_t *tab, 
     uint32_t v;
     if (e < OPTAB_WORDS) {
         v = optab_entry(e, syms + 2 * (size_t)pass * FK);
+    } else if (e >= PASSTAB_CZ) {
+        // upper bound of state 0's metric growth over the pass (PASSTAB_CZ); the other words of the tail are padding
+        v = 0;
+        if (e == PASSTAB_CZ)
+            for (int t = 0; t < FK; t++) {
+                const uint8_t *sp = syms + 2 * ((size_t)pass * FK + t);
+                v += (uint32_t)((G1FLIP ? 255 - sp[0] : sp[0]) + (G2FLIP ? 255 - sp[1] : sp[1]));
+            }
     } else {
         const int t = e - OPTAB_WORDS;
         const long long stage = (long long)pass * FK + t;
@@ -381,7 +389,7 @@ __device__ __forceinline__ void slot_reset(PassSlot &s, int pass)
     s.done_word = done_word_fresh(pass);          // no tile done yet, tagged with the pass the slot now serves
 }
 
-__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T, int no_discard)
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T, int no_discard, const uint32_t *passtab)
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
@@ -392,8 +400,11 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long lon
     pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
     pc.maxR_prev = c->maxR;
     for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i], i); pc.slot[i].pass_word = 0; }
-    const int careful0 = force_careful || (c->R0 + 510ll * FK >= RENORM_TRIGGER);
-    const int careful1 = force_careful || (c->R0 + 510ll * 2 * FK >= RENORM_TRIGGER);
+    pc.passtab = passtab;
+    // state 0 can gain at most cz per pass (PASSTAB_CZ): a pass that cannot reach the trigger need not record per-stage minima
+    const long long cz0 = passtab[PASSTAB_CZ], cz1 = npasses > 1 ? passtab[PASSTAB_WORDS + PASSTAB_CZ] : 510ll * FK;
+    const int careful0 = force_careful || (c->R0 + cz0 >= RENORM_TRIGGER);
+    const int careful1 = force_careful || (c->R0 + cz0 + cz1 >= RENORM_TRIGGER);
     pc.slot[0].pass_word = make_pass_word(0, careful0, c->sub, !no_discard && discard_ok(c->maxR, c->spread, FK));
     pc.slot[1].pass_word = make_pass_word(1, careful1, 0, !no_discard && discard_ok(c->maxR, c->spread, 2 * FK));
     int stop = npasses;
@@ -460,7 +471,9 @@ __device__ void resolve_persist(Ctl *c, int n)
         PassSlot &nx = pc.slot[(n + 2) % PSLOTS];
         slot_reset(nx, n + 2);
         const int sub1 = pass_word_sub(*(volatile unsigned long long *)&pc.slot[(n + 1) % PSLOTS].pass_word);
-        const int careful2 = pc.force_careful || ((long long)z + O + 510ll * 2 * FK >= RENORM_TRIGGER);
+        long long cz = 510ll * 2 * FK;
+        if (n + 2 < pc.npasses) cz = (long long)pc.passtab[(size_t)(n + 1) * PASSTAB_WORDS + PASSTAB_CZ] + pc.passtab[(size_t)(n + 2) * PASSTAB_WORDS + PASSTAB_CZ];
+        const int careful2 = pc.force_careful || ((long long)z + O + cz >= RENORM_TRIGGER);
         if (!careful2 && (long long)mx + O + 510ll * 2 * FK > 32767) {
             if (n + 2 < pc.stop_pass) pc.stop_pass = n + 2;
         }
@@ -734,7 +747,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     for (int s = 0; s < m.nctx; s++) {
         const PersistArgs &a = m.ctx[s];
         k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
-        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0, m.no_discard);
+        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0, m.no_discard, a.passtab);
     }
     const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
     const int grid = (int)(items < nslots ? items : nslots);

@@ -171,6 +171,7 @@ struct PersistCtl {
     int npasses;
     int force_careful;
     int no_discard;         // passes never drop their consumed input lines from the L2 (option)
+    const uint32_t *passtab; // the launch's per-pass tables (the resolver reads the growth bound of state 0 from them)
     long long Ostore;       // R = P_stored + Ostore for the output of the last resolved pass
     long long maxR_prev;    // largest reference metric at the output of the last resolved pass
     PassSlot slot[PSLOTS];

@@ -128,7 +128,12 @@ static_assert(FK == 8 && FR == 4, "packed labels are written out for 8 stages in
 // Operand table in shared memory: optab[(t-1)*32 + beta*8 + {0..3: X[beta^i], 4..7: K[beta^i]}].
 // The per-pass table in global memory (PassTab) carries it plus the ring rows of the pass's eight stages.
 constexpr int OPTAB_WORDS = FK * 32;
-constexpr int PASSTAB_WORDS = OPTAB_WORDS + FK;      // 264 words = 66 x 16 bytes
+// Word OPTAB_WORDS + FK: the most the metric of state 0 can grow over the pass -- the cost of staying in state 0 for all its stages,
+// sum of s0 + (255 - s1) (the all-zero transition expects symbols (G1FLIP, G2FLIP) = (0, 1), viterbi224_sse2.c:75-76,292): the
+// survivor of state 0 is the minimum over two candidates one of which is that transition.  The resolver predicts from it which
+// passes can reach the renormalisation trigger (and have to record per-stage minima).
+constexpr int PASSTAB_CZ = OPTAB_WORDS + FK;
+constexpr int PASSTAB_WORDS = OPTAB_WORDS + FK + 4;  // 268 words = 67 x 16 bytes
 
 // Entry `e` (0 .. FK*32) of the operand table for the pass whose symbols are sym[2*(t-1)], sym[2*(t-1)+1].
 template <typename SymPtr>
