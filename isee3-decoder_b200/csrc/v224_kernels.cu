@@ -258,6 +258,10 @@ template __global__ void k_acs_single<true>(SingleArgs);
 // The metrics stay below 2^16 in every half (spread <= MAX_FAST_SPREAD, checked on entry), so packed adds cannot carry.
 constexpr uint32_t NUNITS = NBFLY / 8;            // 2^19
 constexpr int SINGLE_FAST_THREADS = 512;
+#ifndef V224_SINGLE_DEPTH
+#define V224_SINGLE_DEPTH 2
+#endif
+constexpr int SINGLE_FAST_DEPTH = V224_SINGLE_DEPTH;   // units a thread has in flight (all their loads issued before the first add)
 
 struct FastUnit { uint4 va, vc; uint32_t u; };
 
@@ -374,17 +378,17 @@ __global__ void __launch_bounds__(SINGLE_FAST_THREADS, 2) k_acs_single_fast(Sing
     const uint32_t wu1 = (uint32_t)(((unsigned long long)(wblock + 1) * (NUNITS / 32)) / nwork) * 32u;
     uint32_t mnp = 0xffffffffu, mxp = 0;
     const uint4 *old4 = reinterpret_cast<const uint4 *>(oldm);
-    for (uint32_t base = wu0; base < wu1; base += 2 * SINGLE_FAST_THREADS) {
-        FastUnit f[2];
-        bool on[2];
+    for (uint32_t base = wu0; base < wu1; base += SINGLE_FAST_DEPTH * SINGLE_FAST_THREADS) {
+        FastUnit f[SINGLE_FAST_DEPTH];
+        bool on[SINGLE_FAST_DEPTH];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < SINGLE_FAST_DEPTH; k++) {
             f[k].u = base + k * SINGLE_FAST_THREADS + threadIdx.x;
             on[k] = f[k].u < wu1;                       // whole warps switch on and off together (the range is warp-aligned)
             if (on[k]) { f[k].va = old4[f[k].u]; f[k].vc = old4[f[k].u + NUNITS]; }
         }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < SINGLE_FAST_DEPTH; k++) {
             if (!on[k]) continue;
             uint32_t dec, n00;
             fast_unit(f[k], sub2, X0, newm, ring_row, mnp, mxp, dec, n00);
