@@ -855,3 +855,70 @@ def test_two_host_threads_decode_concurrently_on_one_gpu():
     assert not errors, errors
     for i in range(2):
         assert np.array_equal(got[i], want[i]), i
+
+
+@pytest.mark.parametrize("name,lo,hi,pins", [
+    ("wide spread, fast path but no L2 discard", -32000, -9500, [[0, -20000]]),
+    ("spread beyond the fast path: exact integer stages until it narrows", -32768, -5000, [[0, -32768], [77, 2000]]),
+    ("close to saturation with a small spread: careful passes and saturating stages", 22500, 24200, [[0, 23000]]),
+    ("state 0 just below the renormalisation trigger, minimum far below", -30000, 24000, [[0, 24990], [4194304, 24500]]),
+])
+def test_synthetic_states_at_the_limits_of_the_fast_path(name, lo, hi, pins):
+    """Mid-stream states loaded through v224x_set_state that sit at the edges the fused kernel's bookkeeping watches -- spread near
+    MAX_FAST_SPREAD (passes may run but must keep their input: no L2 discard), spread beyond it, metrics near int16 saturation,
+    state 0 at the renormalisation trigger -- then 88 stages in chunks that mix fused passes, remainders and the lockstep path.
+    Renormalisation counts, min / max metrics, every path metric and every decision row equal the CPU checker."""
+    Checker = pyoracle.best_cpu_decoder()
+    rng = np.random.default_rng(len(name))
+    syms = rng.integers(0, 256, 2 * 96, dtype=np.uint8)
+    script = [["create", 96], ["init", 0], ["set_state", 31, lo, hi, pins, 1234, 5], ["update", 0, 16], ["minmax"], ["update", 16, 3],
+              ["update", 19, 48], ["minmax"], ["update", 67, 21], ["decodebit", 70, -1], ["chainback", 90, 0]]
+    got = run_script(gpu_factory(), script, syms)
+    ref = run_script(lambda n: Checker(n), script, syms)
+    compare_outcomes(got, ref, name)
+    got2 = run_script(gpu_factory(tile32=0, grid_limit=444), script, syms)       # the 64-column build (the one that discards)
+    compare_outcomes(got2, ref, name + " / 64-column tiles")
+
+
+def test_lockstep_decoders_in_limit_states_leave_lockstep_exactly():
+    """Four decoders in one lockstep launch (the 64-column build, which drops consumed metric lines from the L2), three of them in
+    synthetic states the bookkeeping has to treat specially: near int16 saturation (passes are declined, exact saturating stages
+    take over, the decoder leaves lockstep), a spread near the fast path's limit (passes run but keep their input), state 0 at
+    the renormalisation trigger.  Each decoder ends exactly where the CPU checker ends on its own stream."""
+    Checker = pyoracle.best_cpu_decoder()
+    n, ring = 120, 128
+    rng = np.random.default_rng(99)
+    streams = [rng.integers(0, 256, 2 * n, dtype=np.uint8) for _ in range(4)]
+    states = [None, (27000, 32700, [[0, 15000], [4194304, 15000]]), (-32000, -9500, [[0, -20000]]), (-30000, 24000, [[0, 24990]])]
+    decs = [v224.Viterbi224(ring) for _ in range(4)]
+    try:
+        dptr, want = [], []
+        for i, (d, sy) in enumerate(zip(decs, streams)):
+            p = d.dev_alloc(sy.size)
+            d.h2d(p, sy)
+            dptr.append(p)
+            m = None
+            if states[i]:
+                lo, hi, pins = states[i]
+                m = np.random.default_rng(40 + i).integers(lo, hi + 1, 1 << 23).astype(np.int16)
+                for idx, val in pins:
+                    m[idx] = val
+                d.set_state(m, 777, 3)
+            with Checker(ring) as o:
+                o.init(0)
+                if m is not None:
+                    o.set_state(m, 777, 3)
+                r = o.update_blk(sy, n)
+                first = 3 if m is not None else 0
+                want.append((r, o.get_metrics(), [crc(o.get_row((first + k) % ring)) for k in range(n)], o.min_metric(), o.max_metric()))
+        ren = v224.Viterbi224.update_multi_dev(decs, dptr, n)
+        for i, d in enumerate(decs):
+            first = 3 if states[i] else 0
+            assert ren[i] == want[i][0], i
+            assert np.array_equal(d.get_metrics(), want[i][1]), i
+            assert [crc(d.get_row((first + k) % ring)) for k in range(n)] == want[i][2], i
+            assert (d.min_metric(), d.max_metric()) == (want[i][3], want[i][4]), i
+        assert decs[1].stats()["sat_stages"] > 0
+    finally:
+        for d in decs:
+            d.delete()
