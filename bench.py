@@ -644,6 +644,8 @@ def main():
                 "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": scaling_of(args, world), "vs_baseline": None, "dtype": "u16",
                 "data": "synthetic", "config": workload_config(args, world, total_bits),
                 "state_updates_per_s": value * (1 << 23),
+                "per_gpu": {"value": value / world, "unit": "bits/s", "note": "whole-job value / GPUs: what weak scaling (the same bits per GPU, "
+                            "--scaling weak) measures, since the rate does not depend on the stream's length"},
                 "e2e": {"value": e2e, "unit": "bits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(npairs),
                         "ms_per_step": ms_e2e_max / args.steps,
                         "includes": "host pairing / phase flip over the whole stream (v224x_pair_symbols), H2D of every rank's pairs from pinned "
