@@ -175,6 +175,7 @@ struct TileInfo {
     int careful;
     int n, s;            // pass and decoder (the protocol warps' own bookkeeping)
     uint32_t lab;        // packed_tile_labels(tau): the tile's part of every stage's branch label
+    int measure;         // reduce min / max of the tile's output (pass_word)
     int discard;         // the pass cannot be invalidated: its input lines may be dropped from the L2 once they are in shared memory
 };
 // Tile k of a CTA uses bookkeeping slot k % NSLOT (info, pass table, full/done barriers) and data buffer k % XCHG_BUFS.
@@ -356,8 +357,8 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 }
             }
         }
-        // ---- statistics of the final stage ----
-        {
+        // ---- statistics of the final stage (only in the passes that measure; state 0 always) ----
+        if (CAREFUL || ti.measure) {
             const uint32_t mn = __reduce_min_sync(0xffffffffu, tile_min(A));
             const uint32_t mx = __reduce_max_sync(0xffffffffu, tile_max(A));
             if ((tid & 31) == 0) {
@@ -365,9 +366,9 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
                 atomicMin(&st->minP[FK][b][0], mn);
                 atomicMax(&st->maxP[b][0], mx);
             }
-            __syncwarp();
-            if (tau == 0 && tid < FK) st->s0[tid + 1] = s0[tid + 1];          // tid 0 wrote them (same warp)
         }
+        __syncwarp();
+        if (tau == 0 && tid < FK) st->s0[tid + 1] = s0[tid + 1];              // tid 0 wrote them (same warp)
         TRACE(trace_n, tau, 5);
     }
 }
@@ -389,7 +390,7 @@ __device__ __forceinline__ void slot_reset(PassSlot &s, int pass)
     s.done_word = done_word_fresh(pass);          // no tile done yet, tagged with the pass the slot now serves
 }
 
-__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T, int no_discard, const uint32_t *passtab)
+__global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long long expected_T, int no_discard, const uint32_t *passtab, int measure_all)
 {
     PersistCtl &pc = c->pc;
     pc.next_item = 0;
@@ -397,6 +398,9 @@ __global__ void k_persist_begin(Ctl *c, int npasses, int force_careful, long lon
     pc.npasses = npasses;
     pc.force_careful = force_careful;
     pc.no_discard = no_discard;
+    pc.measure_all = measure_all;
+    pc.lbP = (unsigned)c->sub;                 // the buffer the launch starts from: min >= sub, max <= sub + spread (exact after a measured pass)
+    pc.ubP = (unsigned)(c->sub + c->spread);
     pc.Ostore = c->O - c->sub;                 // external convention: R = (P - sub) + O
     pc.maxR_prev = c->maxR;
     for (int i = 0; i < PSLOTS; i++) { slot_reset(pc.slot[i], i); pc.slot[i].pass_word = 0; }
@@ -449,11 +453,22 @@ __device__ void resolve_persist(Ctl *c, int n)
             maxR -= minR + 32768;
         }
     }
-    const unsigned mn = stats_min(sl.st, FK), mx = stats_max(sl.st), z = *(volatile unsigned *)&sl.st.s0[FK];
-    if (valid && (mn == 0xffffffffu || mx < mn)) { c->error |= 2; valid = false; }
+    const unsigned z = *(volatile unsigned *)&sl.st.s0[FK];
+    unsigned mn, mx;
+    if (pass_word_measure(pw) || careful) {
+        mn = stats_min(sl.st, FK);
+        mx = stats_max(sl.st);
+        if (valid && (mn == 0xffffffffu || mx < mn)) { c->error |= 2; valid = false; }
+    } else {
+        // not measured: the pass loaded P - sub (sub <= lbP by construction); a metric never decreases, the largest grows by <= 255 per stage
+        mn = pc.lbP - (unsigned)sub;
+        mx = pc.ubP - (unsigned)sub + (unsigned)(MAX_GROWTH_PER_STAGE * FK);
+    }
     if (valid && (long long)mx - mn > MAX_FAST_SPREAD) valid = false;
     if (valid) {
         pc.Ostore = O;
+        pc.lbP = mn;
+        pc.ubP = mx;
         pc.maxR_prev = (long long)mx + O;
         c->renormals += renormals;
         c->renorm_count += count;
@@ -480,7 +495,15 @@ __device__ void resolve_persist(Ctl *c, int n)
         __threadfence();                                                   // the reset slot before the word that opens it
         // (the statistics are pass n's: pass n+2 ends 2 * FK stages later)
         const int discard2 = !pc.no_discard && discard_ok((long long)mx + O, (long long)mx - mn, 2 * FK);
-        *(volatile unsigned long long *)&nx.pass_word = make_pass_word(n + 2, careful2, (int)mn - sub1, discard2);   // sub <= min of pass n+1's output
+        // Pass n+2 reduces min / max if it is careful, periodically, at the end of the launch (the host and the one-stage kernel
+        // then see exact values), and whenever its output could come near anything the values are compared with -- the
+        // saturation watch, the spread limit, the 16 bits of P: the bounds below hold for pass n+2's output (two passes of
+        // growth), so every comparison that can go the other way is made on measured values and a loose bound never costs a decision.
+        const long long slack = MAX_GROWTH_PER_STAGE * FK * 2;
+        const int measure2 = pc.measure_all || careful2 || (n + 2) % MEASURE_EVERY == MEASURE_EVERY - 1 || n + 2 >= pc.npasses - 1 ||
+                             (long long)mx + O + 510ll * 2 * FK + slack > 32767 || (long long)mx - mn + 510ll * 2 * FK + slack > MAX_FAST_SPREAD ||
+                             (long long)mx + slack > 40000;
+        *(volatile unsigned long long *)&nx.pass_word = make_pass_word(n + 2, careful2, (int)mn - sub1, discard2, measure2);   // sub <= min of pass n+1's output
     } else {
         // the pass (and anything that already consumed its output) is discarded; its input buffer is intact
         if (n < pc.stop_pass) { pc.stop_pass = n; c->n_invalidated++; }
@@ -576,6 +599,7 @@ __device__ void producer_warp(FusedSmem &sm, const MultiArgs &m)
             ti.sub2 = (uint32_t)pass_word_sub(pw) * 0x10001u;
             ti.careful = (int)pass_word_careful(pw);
             ti.discard = (int)pass_word_discard(pw);
+            ti.measure = (int)pass_word_measure(pw);
             ti.go = stopped ? 0 : 1;
             ti.n = n;
             ti.s = (int)s;
@@ -747,7 +771,7 @@ cudaError_t launch_persist(const MultiArgs &m, cudaStream_t st)
     for (int s = 0; s < m.nctx; s++) {
         const PersistArgs &a = m.ctx[s];
         k_build_passtab<<<m.npasses, PASSTAB_WORDS, 0, st>>>(a.passtab, a.syms + 2 * (size_t)a.pos0, m.npasses, a.T0, a.len, a.row_fmt);
-        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0, m.no_discard, a.passtab);
+        k_persist_begin<<<1, 1, 0, st>>>(a.ctl, m.npasses, a.force_careful, a.T0, m.no_discard, a.passtab, m.measure_all);
     }
     const long long items = (long long)m.npasses * m.nctx * FUSED_TILES;
     const int grid = (int)(items < nslots ? items : nslots);

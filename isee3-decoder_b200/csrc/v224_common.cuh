@@ -134,7 +134,11 @@ __host__ __device__ inline unsigned stats_max(const PassStats &s)
 // warp has to poll, so that one round of parallel loads decides "may this tile start":
 //   done_word = [63:24] tiles done per class, 10 bits each (class = tile index mod TILE_CLASSES) | [23:11] pass number mod 2^13
 //               | [10:0] tiles done      (the pass tag is written when the slot is reset for that pass)
-//   pass_word = (pass number + 1) << 32 | careful << 31 | discard << 30 | sub     published by the resolver of pass n-2 (or the launch)
+//   pass_word = (pass number + 1) << 32 | careful << 31 | discard << 30 | measure << 29 | sub     published by the resolver of pass n-2 (or the launch)
+//               measure: the pass's tiles reduce the minimum and maximum of its output.  They are only needed to keep bounds tight (the
+//               subtraction that keeps P small, the saturation / spread watch), so most passes skip them and the resolver carries
+//               rigorous bounds instead: a metric never decreases, and the largest one grows by at most 255 per stage (a survivor is
+//               the smaller of two candidates whose branch metrics add up to 510)
 //               discard: the pass cannot be invalidated (the launch / resolver has proved that the reference cannot saturate before it
 //               ends and that its metric spread stays in range), so its tiles may drop their input lines from the L2
 struct PassSlot {
@@ -142,12 +146,15 @@ struct PassSlot {
     unsigned long long done_word;
     unsigned long long pass_word;
 };
-__host__ __device__ inline unsigned long long make_pass_word(int n, int careful, int sub, int discard = 0)
+__host__ __device__ inline unsigned long long make_pass_word(int n, int careful, int sub, int discard = 0, int measure = 1)
 {
     return ((unsigned long long)(unsigned)(n + 1) << 32) | ((unsigned long long)(careful ? 1u : 0u) << 31) |
-           ((unsigned long long)(discard ? 1u : 0u) << 30) | ((unsigned)sub & 0x3fffffffu);
+           ((unsigned long long)(discard ? 1u : 0u) << 30) | ((unsigned long long)(measure ? 1u : 0u) << 29) | ((unsigned)sub & 0x1fffffffu);
 }
-__host__ __device__ inline int pass_word_sub(unsigned long long w) { return (int)(w & 0x3fffffffu); }
+__host__ __device__ inline int pass_word_sub(unsigned long long w) { return (int)(w & 0x1fffffffu); }
+__host__ __device__ inline bool pass_word_measure(unsigned long long w) { return ((w >> 29) & 1u) != 0; }
+constexpr int MEASURE_EVERY = 4;                   // a pass in this many reduces min / max even when nothing else asks for it
+constexpr long long MAX_GROWTH_PER_STAGE = 255;    // of the largest path metric (see pass_word)
 __host__ __device__ inline bool pass_word_careful(unsigned long long w) { return ((w >> 31) & 1u) != 0; }
 __host__ __device__ inline bool pass_word_discard(unsigned long long w) { return ((w >> 30) & 1u) != 0; }
 // A pass may drop its input lines only if nothing can invalidate it: the reference cannot saturate before the pass ends (the
@@ -171,6 +178,8 @@ struct PersistCtl {
     int npasses;
     int force_careful;
     int no_discard;         // passes never drop their consumed input lines from the L2 (option)
+    int measure_all;        // every pass reduces min / max (option "measure_all")
+    unsigned lbP, ubP;      // bounds of the stored metrics (P) of the last resolved pass's output: min >= lbP, max <= ubP
     const uint32_t *passtab; // the launch's per-pass tables (the resolver reads the growth bound of state 0 from them)
     long long Ostore;       // R = P_stored + Ostore for the output of the last resolved pass
     long long maxR_prev;    // largest reference metric at the output of the last resolved pass

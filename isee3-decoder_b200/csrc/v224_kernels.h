@@ -26,6 +26,7 @@ constexpr int MAX_CTX = 4;
 struct MultiArgs {
     int nctx;
     int npasses;             // per context
+    int measure_all;         // every pass reduces the min / max of its output (option "measure_all")
     int no_discard;          // never drop consumed metric lines from the L2 (option "no_discard")
     int grid_limit;          // 0: one CTA per resident slot (148 SMs x CTAs per SM); > 0: at most this many CTAs; < 0: -grid_limit CTAs per SM
     PersistArgs ctx[MAX_CTX];

@@ -145,6 +145,7 @@ struct Decoder {
     long long spec_T, spec_bit;
     int no_mailbox;            // option: always take the synchronous path
     int no_discard;            // option: fused passes never drop their consumed input lines from the L2
+    int measure_all;           // option: every fused pass reduces the min / max of its output
     int slow_single;           // option: the scalar form of the one-stage kernel
     int fused_rows;            // a fused pass has written rows into the ring since it was last cleared (their layout differs)
     // segmented stream decode: auxiliary decoders (owned, cached), snapshot of this decoder's metrics at its hand-over point
@@ -344,6 +345,7 @@ int recycle(Decoder *d)
     d->spec_want = d->spec_valid = 0;
     d->slow_single = 0;
     d->no_discard = 0;
+    d->measure_all = 0;
     d->fused_rows = 0;                       // every row it ever wrote is cleared below, tags included
     d->tile32 = TILE32_DEFAULT;
     d->chain_seg = 64;
@@ -399,6 +401,7 @@ int update_core(Decoder *d, const uint8_t *dev_syms, int nbits, int arg_s0 = -1,
                 m.nctx = 1;
                 m.npasses = npasses;
                 m.no_discard = d->no_discard;
+                m.measure_all = d->measure_all;
                 // a decoder alone is latency bound (pass n+1 needs all of pass n).  64-column tiles: one CTA per SM finishes a tile
                 // sooner than three sharing the SM, and the pass with it (13.6 instead of 15.3 us); 32-column tiles (the default
                 // for a lone decoder): half the tile latency and finer dependencies, 12.9 us (profiles/r02_probe_*.txt)
@@ -477,6 +480,7 @@ int multi_update_core(Decoder **ds, const unsigned char *const *dev_syms, int nc
         m.nctx = nctx;
         m.npasses = npasses;
         m.no_discard = d0->no_discard;
+        m.measure_all = d0->measure_all;
         m.grid_limit = d0->grid_limit > 0 ? d0->grid_limit : (nctx == 1 ? -1 : 0);
         const bool mt32 = d0->tile32 == 2 || d0->tile32 == 4;        // measurement knobs: lockstep decoders on the 32-column-tile builds
         for (int s = 0; s < nctx; s++) {
@@ -1613,6 +1617,7 @@ int v224x_set_option(void *p, const char *key, long long value)
     else if (!strcmp(key, "tile32")) d->tile32 = (int)value;
     else if (!strcmp(key, "slow_single")) d->slow_single = (int)value;
     else if (!strcmp(key, "no_discard")) d->no_discard = (int)value;
+    else if (!strcmp(key, "measure_all")) d->measure_all = (int)value;
     else if (!strcmp(key, "chain_seg")) d->chain_seg = (int)std::max(8ll, value);
     else if (!strcmp(key, "chain_warm")) d->chain_warm = (int)std::max(0ll, value);
     else { set_err("unknown option %s", key); return -1; }

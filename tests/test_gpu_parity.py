@@ -53,7 +53,7 @@ def test_golden_default_path(golden_cases, name):
                                   {"chain_seg": 64, "chain_warm": 16},
                                   {"tile32": 1}, {"tile32": 0}, {"tile32": 1, "force_careful": 1}, {"tile32": 1, "per_pass_launch": 1},
                                   {"tile32": 1, "grid_limit": 97}, {"no_mailbox": 1}, {"slow_single": 1},
-                                  {"tile32": 2}, {"no_discard": 1}, {"tile32": 0, "grid_limit": 444}])
+                                  {"tile32": 2}, {"no_discard": 1}, {"tile32": 0, "grid_limit": 444}, {"measure_all": 1}])
 @pytest.mark.parametrize("name", ["awgn1db_648_chunks", "erasure_304", "ringwrap_len40_200", "saturation_forced_72", "stream_d64_320"])
 def test_golden_kernel_variants(golden_cases, name, opts):
     case = golden_cases[name]
