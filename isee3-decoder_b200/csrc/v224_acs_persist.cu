@@ -186,6 +186,9 @@ struct TileInfo {
 #ifndef V224_NSLOT
 #define V224_NSLOT 2
 #endif
+#ifndef V224_SUB_SKIP
+#define V224_SUB_SKIP 0
+#endif
 constexpr int NSLOT = V224_NSLOT;
 constexpr int CTA_THREADS = FUSED_THREADS + 64;              // compute warps + producer warp + retirer warp
 struct __align__(128) FusedSmem {
@@ -264,7 +267,28 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
         uint32_t thr, g;
         round1_map(tid, thr, g);
         const uint32_t G = tau * FUSED_COLGROUPS + g;              // global column group: columns COLW*G ..
-        if (BULK_LOAD) {
+        if (BULK_LOAD && V224_SUB_SKIP) {
+            // (A/B) most passes carry sub == 0 (a subtraction follows a MEASURED pass two passes later): skip the 16 * NQ subtractions then
+#pragma unroll
+            for (int mh = 0; mh < 16; mh++) {
+                const uint32_t e = (mh * 16 + thr) * FUSED_COLGROUPS + g;
+                if (NQ == 4) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(xbuf)[e];
+                    A[mh][0] = v.x; A[mh][1] = v.y; A[mh][NQ - 2] = v.z; A[mh][NQ - 1] = v.w;
+                } else if (NQ == 2) {
+                    const uint2 v = reinterpret_cast<const uint2 *>(xbuf)[e];
+                    A[mh][0] = v.x; A[mh][NQ - 1] = v.y;
+                } else {
+                    A[mh][0] = xbuf[e];
+                }
+            }
+            if (sub != 0) {
+#pragma unroll
+                for (int mh = 0; mh < 16; mh++)
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) A[mh][q] -= sub;
+            }
+        } else if (BULK_LOAD) {
             // the protocol warp's bulk copies put the tile into this buffer (row m at 128 m bytes) before the hand-over
 #pragma unroll
             for (int mh = 0; mh < 16; mh++) {

@@ -48,6 +48,11 @@ static inline uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel)
     }
     return r;
 }
+static inline uint32_t f_add_u16x2(uint32_t a, uint32_t b)
+{
+    return (((a & 0xffff) + (b & 0xffff)) & 0xffff) | (((a >> 16) + (b >> 16)) << 16);
+}
+static inline uint32_t f_sub_add(uint32_t c, uint32_t a, uint32_t k) { return c - a + k; }
 static inline uint32_t f_minu2(uint32_t a, uint32_t b)
 {
     uint32_t lo = (a & 0xffff) < (b & 0xffff) ? (a & 0xffff) : (b & 0xffff);
@@ -74,9 +79,35 @@ V224_HD uint32_t f_prmt(uint32_t a, uint32_t b, uint32_t sel)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
+V224_HD uint32_t f_add_u16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }                                // VIADD.16x2 (ALU pipe)
+V224_HD uint32_t f_sub_add(uint32_t c, uint32_t a, uint32_t k)                                                // c - a + k, kept together
+{
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tsub.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(r) : "r"(c), "r"(a), "r"(k));
+    return r;
+}
 V224_HD uint32_t f_minu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }                                   // VIMNMX.U16x2
 V224_HD uint32_t f_maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 }
+#endif
+
+// Pipe balance of the butterfly (profiles/r02_ab_pipe_balance.txt).  The SM has two integer-capable pipes, both 16 lanes wide: ALU
+// (VIADDMNMX, PRMT, LOP3, IADD3, VIADD.16x2) and FMA-heavy (IMAD.IADD -- what ptxas makes of a plain two-input add when the ALU
+// pipe already carries the rest).  Written with two-input adds only, a pair of packed butterflies is 5 FMA-heavy + 4 ALU
+// instructions, and ncu shows FMA-heavy as the busier pipe (63 % against 58 %).  Bit pidx of V224_IADD3_MASK (and bit q of
+// V224_IADD3_QMASK) turns a pair's three adds  u = c - a, u + K0, u + K1  into two three-input adds  c - a + K0, c - a + K1
+// (IADD3, ALU pipe): one instruction fewer, 3 off the FMA-heavy pipe, 2 onto the ALU pipe.  One pair index in eight (2 of a stage's
+// 16 pairs) balances the pipes and is the measured optimum (8.35 -> 8.14 us per pass with 4 decoders in lockstep, 13.62 -> 13.40
+// for one alone); more of them overload the ALU pipe.  V224_ALU_ADD_MASK moves c + x of the selected pairs onto the ALU pipe as a
+// packed VIADD.16x2 instead (same value: no half overflows) -- measured, smaller gain, off.
+#ifndef V224_ALU_ADD_MASK
+#define V224_ALU_ADD_MASK 0
+#endif
+#ifndef V224_IADD3_MASK
+#define V224_IADD3_MASK 0x01
+#endif
+#ifndef V224_IADD3_QMASK
+#define V224_IADD3_QMASK 0xff
 #endif
 
 namespace V224_NS {
@@ -183,12 +214,18 @@ V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *o
             const uint32_t X = Xv[c], Y = Xv[c ^ 3], K0 = Kv[c], K1 = Kv[c ^ 3];
             const uint32_t a = A[ia][q], cc = A[ic][q];
             // m0 = a+x, m1 = c+y, m2 = a+y, m3 = c+x          (viterbi224_sse2.c:296-299)
-            const uint32_t t0 = cc + Y, t1 = cc + X;
+            const uint32_t t0 = cc + Y, t1 = ((V224_ALU_ADD_MASK >> pidx) & 1) ? f_add_u16x2(cc, X) : cc + X;
             // decision0 = m0 > m1  <=>  (c - a) - delta < 0  <=> bit15 of D0 clear   (:316)
             // decision1 = m2 > m3  <=>  (c - a) + delta < 0  <=> bit15 of D1 clear   (:317)
-            const uint32_t u = cc - a;
-            D0[q] = u + K0;
-            D1[q] = u + K1;
+            if (((V224_IADD3_MASK >> pidx) & 1) && ((V224_IADD3_QMASK >> q) & 1)) {
+                // one three-input add per decision word (IADD3, ALU pipe) for the pairs that balance the two integer pipes
+                D0[q] = f_sub_add(cc, a, K0);
+                D1[q] = f_sub_add(cc, a, K1);
+            } else {
+                const uint32_t u = cc - a;
+                D0[q] = u + K0;
+                D1[q] = u + K1;
+            }
             A[ia][q] = f_addmin_u16x2(a, X, t0);          // min(m0, m1) -> state 2b    (:319)
             A[ic][q] = f_addmin_u16x2(a, Y, t1);          // min(m2, m3) -> state 2b+1  (:320)
         }
