@@ -186,8 +186,17 @@ struct TileInfo {
 #ifndef V224_NSLOT
 #define V224_NSLOT 2
 #endif
+// Two small savings in the tile body, measured together with the pipe balance of the butterfly (profiles/r02_ab_pipe_balance.txt):
+// V224_SUB_SKIP: most passes carry sub == 0 (a subtraction follows a MEASURED pass two passes later), and the 16 * NQ subtractions
+// of the load are skipped then (warp-uniform branch); V224_OPERAND_PREFETCH: 1 = a stage's operands are loaded by the PREVIOUS stage,
+// right after its butterflies (the registers are free there), so that a stage does not open with two shared loads its first adds wait
+// for; n >= 2 = before pair index n - 2 of the butterflies (ptxas sinks those loads back next to the stores: no gain).  Together
+// 8.15 -> 8.06 us per pass with 4 decoders in lockstep.
 #ifndef V224_SUB_SKIP
-#define V224_SUB_SKIP 0
+#define V224_SUB_SKIP 1
+#endif
+#ifndef V224_OPERAND_PREFETCH
+#define V224_OPERAND_PREFETCH 1
 #endif
 constexpr int NSLOT = V224_NSLOT;
 constexpr int CTA_THREADS = FUSED_THREADS + 64;              // compute warps + producer warp + retirer warp
@@ -232,12 +241,26 @@ __global__ void __launch_bounds__(PASSTAB_WORDS) k_build_passtab(uint32_t *tab, 
 // ------------------------------------------------------------------------------------------
 // compute warps: one tile, eight stages
 // ------------------------------------------------------------------------------------------
+// Xv / Kv: the stage's operands, loaded by the previous stage (V224_OPERAND_PREFETCH above); on return those of the next stage.
 template <int T, bool CAREFUL>
 __device__ __forceinline__ void fused_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *tab, uint32_t *s0, uint32_t *ring_chunk,
-                                            PassStats *st)
+                                            PassStats *st, uint32_t (&Xv)[4], uint32_t (&Kv)[4])
 {
     uint32_t dw[NQ];
-    acs_stage<T>(A, labels, tab, dw);
+    if (V224_OPERAND_PREFETCH >= 2) {
+        // ... or already before pair index V224_OPERAND_PREFETCH - 2 of the butterflies (eight more live registers from there on)
+        uint32_t Xn[4], Kn[4];
+        acs_stage_body<T, V224_OPERAND_PREFETCH - 2>(A, Xv, Kv, dw, labels, tab, Xn, Kn);
+        if (T < FK) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { Xv[i] = Xn[i]; Kv[i] = Kn[i]; }
+        }
+    } else if (V224_OPERAND_PREFETCH) {
+        acs_stage_body<T>(A, Xv, Kv, dw);
+        if (T < FK) stage_operands<(T < FK ? T + 1 : T)>(labels, tab, Xv, Kv);
+    } else {
+        acs_stage<T>(A, labels, tab, dw);
+    }
     // row * 1 MiB + this thread's chunk: one 32 x 32 + 64 multiply-add
     uint32_t *dst;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(dst) : "r"(tab[OPTAB_WORDS + T - 1]), "n"((unsigned)ROWBYTES), "l"(ring_chunk));
@@ -262,13 +285,15 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
     PassStats *st = ti.st;
     uint32_t *ring_chunk = ti.ring + (size_t)(tau * FUSED_THREADS + tid) * NQ;      // see fused_bit_address()
     uint32_t A[16][NQ];
+    uint32_t Xv[4], Kv[4];
+    if (V224_OPERAND_PREFETCH) stage_operands<1>(labels, tab, Xv, Kv);
     {
         // ---- round 1: thread = (ml = thr, g); registers = 16 mh rows x 2*NQ columns ----
         uint32_t thr, g;
         round1_map(tid, thr, g);
         const uint32_t G = tau * FUSED_COLGROUPS + g;              // global column group: columns COLW*G ..
         if (BULK_LOAD && V224_SUB_SKIP) {
-            // (A/B) most passes carry sub == 0 (a subtraction follows a MEASURED pass two passes later): skip the 16 * NQ subtractions then
+            // sub == 0 in most passes: the subtractions are skipped then (V224_SUB_SKIP above)
 #pragma unroll
             for (int mh = 0; mh < 16; mh++) {
                 const uint32_t e = (mh * 16 + thr) * FUSED_COLGROUPS + g;
@@ -319,10 +344,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             }
         }
         TRACE(trace_n, tau, 2);
-        fused_stage<1, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<2, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<3, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<4, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<1, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<2, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<3, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<4, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
         // ---- exchange: rows m = mh*16 + ml ----
         // The exchange happens in place: a thread writes exactly the rows it read (the swizzle only moves elements
         // between lanes of its own warp).  With a single buffer the previous tile's round-2 reads must be over.
@@ -362,10 +387,10 @@ __device__ __forceinline__ void fused_tile(uint32_t *xbuf, const uint32_t *tab, 
             if ((tid & 31) == 0) mbar_arrive(freeb);
         }
         TRACE(trace_n, tau, 3);
-        fused_stage<5, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<6, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<7, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
-        fused_stage<8, CAREFUL>(A, labels, tab, s0, ring_chunk, st);
+        fused_stage<5, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<6, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<7, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
+        fused_stage<8, CAREFUL>(A, labels, tab, s0, ring_chunk, st, Xv, Kv);
         TRACE(trace_n, tau, 4);
         // ---- output: slot (m, j) holds state (j << 8) | m; per column 16 consecutive ml = 32 B, four lanes = one line ----
         {

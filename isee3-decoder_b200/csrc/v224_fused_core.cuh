@@ -189,21 +189,47 @@ V224_HD uint32_t optab_entry(int e, SymPtr sym)
 //   labels       : packed_thread_labels(..) ^ packed_tile_labels(..): the thread's label (flip included) of stage t at bits 2t-2, 2t-1
 //   optab        : shared operand table
 //   dw[NQ]       : returns the 32*NQ decision bits of this thread/stage in fused layout (fused_bit_address())
+// the thread's four packed X and four packed K of stage T (two 128-bit shared loads)
 template <int T>
-V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *optab, uint32_t (&dw)[NQ])
+V224_HD void stage_operands(uint32_t labels, const uint32_t *optab, uint32_t (&Xv)[4], uint32_t (&Kv)[4])
 {
-    constexpr int sb = FR - 1 - ((T - 1) % FR);          // stage bit inside `inner`
-    constexpr int ishift = (T <= FR) ? 19 : 15;           // slot position of `inner`
     // operand row of this thread's label: (T-1)*32 + beta*8 words
     const uint32_t boff = (T == 1 ? (labels << 3) : T <= 2 ? (labels << 1) : (labels >> (2 * (T - 1) - 3))) & 24u;
     const uint32_t *tab = optab + (T - 1) * 32 + boff;
-    uint32_t Xv[4], Kv[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { Xv[i] = tab[i]; Kv[i] = tab[4 + i]; }
+}
+
+// PF_AT >= 0: the operands of stage T + 1 are loaded into Xn / Kn right before pair index PF_AT (labels / optab as for stage_operands)
+template <int T, int PF_AT = -1>
+V224_HD void acs_stage_body(uint32_t (&A)[16][NQ], const uint32_t (&Xv)[4], const uint32_t (&Kv)[4], uint32_t (&dw)[NQ],
+                            uint32_t labels = 0, const uint32_t *optab = nullptr, uint32_t *Xn = nullptr, uint32_t *Kn = nullptr);
+
+template <int T>
+V224_HD void acs_stage(uint32_t (&A)[16][NQ], uint32_t labels, const uint32_t *optab, uint32_t (&dw)[NQ])
+{
+    uint32_t Xv[4], Kv[4];
+    stage_operands<T>(labels, optab, Xv, Kv);
+    acs_stage_body<T>(A, Xv, Kv, dw);
+}
+
+template <int T, int PF_AT>
+V224_HD void acs_stage_body(uint32_t (&A)[16][NQ], const uint32_t (&Xv)[4], const uint32_t (&Kv)[4], uint32_t (&dw)[NQ],
+                            uint32_t labels, const uint32_t *optab, uint32_t *Xn, uint32_t *Kn)
+{
+    constexpr int sb = FR - 1 - ((T - 1) % FR);          // stage bit inside `inner`
+    constexpr int ishift = (T <= FR) ? 19 : 15;           // slot position of `inner`
 #pragma unroll
     for (int w = 0; w < NQ; w++) dw[w] = 0;
 #pragma unroll
     for (int pidx = 0; pidx < 8; pidx++) {
+        if (PF_AT == pidx && T < FK) {
+            constexpr int TN = T < FK ? T + 1 : T;
+            const uint32_t boff = (TN <= 2 ? (labels << 1) : (labels >> (2 * (TN - 1) - 3))) & 24u;
+            const uint32_t *tabn = optab + (TN - 1) * 32 + boff;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { Xn[i] = tabn[i]; Kn[i] = tabn[4 + i]; }
+        }
         const int ia = ((pidx >> sb) << (sb + 1)) | (pidx & ((1 << sb) - 1));
         const int ic = ia | (1 << sb);
         uint32_t D0[NQ], D1[NQ];
