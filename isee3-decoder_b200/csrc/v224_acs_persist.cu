@@ -18,8 +18,8 @@
 // compute threads, up to 5 CTAs per SM, for a decoder running alone.
 //
 // This file is compiled with -Xptxas -O1: at the default level ptxas hoists the decision-bit gather of a whole stage
-// behind the butterflies and spills (~500 bytes per thread at 64 registers); in source order the tile body fits in the
-// 64-column build and spills two registers in the 32-column build (8 bytes stored / 8 loaded per thread: csrc/ptxas.log).
+// behind the butterflies and spills (~500 bytes per thread at 64 registers); in source order the tile body fits in both
+// builds (csrc/ptxas.log).
 #include "v224_common.cuh"
 #include "v224_fused_core.cuh"
 #include "v224_kernels.h"
