@@ -122,12 +122,14 @@ def _emu(name="libfused_emu.so"):
 
 @pytest.mark.parametrize("lib,seed,warm", [("libfused_emu.so", 7, 40), ("libfused_emu.so", 8, 3), ("libfused_emu.so", 9, 25),
                                            ("libfused_emu_t32.so", 7, 40), ("libfused_emu_t32.so", 10, 5),
-                                           ("libfused_emu_t32q1.so", 7, 40), ("libfused_emu_t32q1.so", 11, 9)])
+                                           ("libfused_emu_t32q1.so", 7, 40), ("libfused_emu_t32q1.so", 11, 9),
+                                           ("libfused_emu_addforms.so", 7, 40), ("libfused_emu_addforms.so", 12, 2)])
 def test_fused_pass_index_algebra_against_oracle(built, lib, seed, warm):
     """Host emulation of the fused kernel's arithmetic core (same header, same per-thread data movement and thread
     maps of both register rounds), for both tile widths the library builds (64 columns: lockstep decoders, 32 columns: a
     decoder running alone): metrics, all eight decision rows (through fused_bit_address) and state-0 tracking equal the
-    oracle."""
+    oracle.  "addforms": every pair with the three-input form of the decision words and the packed-halves form of c + x
+    (the library uses them for the pairs that balance the two integer pipes; a half that overflowed would show here)."""
     e = _emu(lib)
     assert e.emu_tile_cols() == (32 if "t32" in lib else 64) and e.emu_nq() == (1 if "q1" in lib else 2)
     fmt_base = e.emu_rowfmt_base()
