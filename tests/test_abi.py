@@ -42,6 +42,31 @@ def test_library_contains_sm100a_code(built):
     assert "sm_100a" in out.stdout
 
 
+def test_fused_pass_is_built_from_the_instructions_the_design_names(built):
+    """DESIGN.md section 3.1 rests on these SASS instructions being what the fused pass compiles to (both tile shapes): the tile's
+    2-D tensor copy and the pass table's bulk copy (TMA), mbarrier waits, the packed add-min of the butterfly, three-input adds
+    with a negated operand for the pairs that balance the integer pipes, 256-bit metric stores, streaming decision stores, and
+    (64-column build) the L2 discard of consumed input lines."""
+    out = subprocess.run(["cuobjdump", "-sass", v224.library_path()], capture_output=True, text=True).stdout
+    body = {}
+    name = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            body[name] = []
+        elif name is not None:
+            body[name].append(line)
+    fused = {n: "\n".join(b) for n, b in body.items() if "k_acs_persist" in n}
+    assert len(fused) == 2, sorted(body)                                   # v224:: (64 columns) and v224t32:: (32 columns)
+    for n, text in fused.items():
+        for needle in ("UTMALDG.2D", "UBLKCP", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "VIADDMNMX.U16x2", "STG.E.ENL2.256", "STG.E.EF"):
+            assert needle in text, (n, needle)
+        assert text.count("VIADDMNMX.U16x2") == 512, n                   # 32 per stage x 8 stages x {careful, plain} tile bodies
+        assert len(re.findall(r"IADD3 R\d+, PT, PT, [^;]*-R\d+", text)) >= 64, n       # c - a + K, 4 per stage x 8 x 2
+        assert "LDL" not in text and "STL" not in text, n                 # no spill in either build (csrc/ptxas.log)
+    assert "CCTL.E.RML2" in next(t for n, t in fused.items() if "t32" not in n)
+
+
 def test_null_handle_conventions(built):
     lib = v224.load_library()
     buf = ctypes.create_string_buffer(16)
